@@ -1,0 +1,222 @@
+// api.cu - the C ABI declared in include/mpcb200.h: argument checks, (n,m) dispatch, launch.
+#include <atomic>
+#include <cstring>
+
+#include "../../../include/mpcb200.h"
+#include "lqr_grad.cuh"
+#include "lqr_step.cuh"
+
+namespace mpcb200 {
+#define MPCB200_INST(n, m)                                                  \
+  int step_f32__##n##_##m(const StepArgs&, int, cudaStream_t);              \
+  int step_f64__##n##_##m(const StepArgs&, int, cudaStream_t);              \
+  int grad_f32__##n##_##m(const GradArgs&, cudaStream_t);                   \
+  int grad_f64__##n##_##m(const GradArgs&, cudaStream_t);                   \
+  size_t smem_f32__##n##_##m(int);                                          \
+  size_t smem_f64__##n##_##m(int);
+#include "instances.def"
+#undef MPCB200_INST
+
+struct Entry {
+  int n, m;
+  int (*step32)(const StepArgs&, int, cudaStream_t);
+  int (*step64)(const StepArgs&, int, cudaStream_t);
+  int (*grad32)(const GradArgs&, cudaStream_t);
+  int (*grad64)(const GradArgs&, cudaStream_t);
+  size_t (*smem32)(int);
+  size_t (*smem64)(int);
+};
+static const Entry kTable[] = {
+#define MPCB200_INST(n, m)                                                                  \
+  {n, m, step_f32__##n##_##m, step_f64__##n##_##m, grad_f32__##n##_##m, grad_f64__##n##_##m, \
+   smem_f32__##n##_##m, smem_f64__##n##_##m},
+#include "instances.def"
+#undef MPCB200_INST
+};
+static const int kTableLen = (int)(sizeof(kTable) / sizeof(kTable[0]));
+
+static const Entry* find(int n, int m) {
+  for (int i = 0; i < kTableLen; ++i)
+    if (kTable[i].n == n && kTable[i].m == m) return &kTable[i];
+  return nullptr;
+}
+
+static std::atomic<uint64_t> g_launches{0};
+
+// per-device opt-in shared memory limit (cached for up to 64 devices)
+static int max_smem_optin() {
+  static int cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev < 0 || dev >= 64) return -1;
+  if (cache[dev] == 0) {
+    int v = 0, major = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+    if (major != 10) return -1;   // sm_100a cubin only
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_dims(const mpcb200_dims* d) {
+  if (d == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (d->B <= 0 || d->T <= 0 || d->n <= 0 || d->m <= 0) return MPCB200_ERR_BAD_DIMS;
+  if (d->F_T != d->T - 1 && d->F_T != d->T) return MPCB200_ERR_BAD_DIMS;
+  return MPCB200_OK;
+}
+
+template <typename R>
+static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C, const R* c, const R* F,
+                     const R* f, const R* x_init, const R* cur_x, const R* cur_u, const R* u_lower,
+                     const R* u_upper, const uint8_t* u_zero_I, R* new_x, R* new_u, R* costs,
+                     R* full_du_norm, R* alphas, R* du_first, int32_t* qp_iters, uint8_t* free_mask, int32_t* status,
+                     R* Ks, R* ks, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if (p == nullptr || C == nullptr || c == nullptr || cur_x == nullptr || cur_u == nullptr)
+    return MPCB200_ERR_NULL_POINTER;
+  if (d->T > 1 && F == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (d->has_f && f == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (d->bounds_kind < 0 || d->bounds_kind > 2) return MPCB200_ERR_BAD_DIMS;
+  if (d->bounds_kind == 2 && (u_lower == nullptr || u_upper == nullptr)) return MPCB200_ERR_NULL_POINTER;
+  if (d->has_zero_mask && u_zero_I == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (d->has_delta_u && d->bounds_kind == 0) return MPCB200_ERR_BAD_DIMS;   // reference lqr_step.py:195
+  if (d->max_ls_iter < 1 || d->pnqp_max_iter < 1) return MPCB200_ERR_BAD_DIMS;
+  if (d->do_rollout) {
+    if (x_init == nullptr || new_x == nullptr || new_u == nullptr || costs == nullptr ||
+        full_du_norm == nullptr || alphas == nullptr)
+      return MPCB200_ERR_NULL_POINTER;
+  } else if (Ks == nullptr || ks == nullptr) {
+    return MPCB200_ERR_NULL_POINTER;
+  }
+  if ((Ks == nullptr) != (ks == nullptr)) return MPCB200_ERR_NULL_POINTER;
+  const Entry* e = find(d->n, d->m);
+  if (e == nullptr) return MPCB200_ERR_UNSUPPORTED_DIMS;
+  const int smem = max_smem_optin();
+  if (smem <= 0) return MPCB200_ERR_NO_DEVICE;
+
+  StepArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = d->B; a.T = d->T; a.F_T = d->F_T;
+  a.has_f = d->has_f ? 1 : 0;
+  a.bounds_kind = d->bounds_kind;
+  a.has_mask = d->has_zero_mask ? 1 : 0;
+  a.has_delta = d->has_delta_u ? 1 : 0;
+  a.max_ls = d->max_ls_iter;
+  a.pnqp_iters = d->pnqp_max_iter;
+  a.do_rollout = d->do_rollout ? 1 : 0;
+  a.u_lo = p->u_lo; a.u_hi = p->u_hi; a.delta_u = p->delta_u; a.ls_decay = p->ls_decay;
+  a.C = C; a.c = c; a.F = F; a.f = f; a.x_init = x_init; a.cur_x = cur_x; a.cur_u = cur_u;
+  a.u_lower = u_lower; a.u_upper = u_upper; a.zero_mask = u_zero_I;
+  a.new_x = new_x; a.new_u = new_u; a.costs = costs; a.full_du_norm = full_du_norm; a.alphas = alphas;
+  a.du_first = du_first; a.qp_iters = qp_iters; a.free_mask = free_mask; a.status = status; a.Ks = Ks; a.ks = ks;
+  // bulk-TMA eligibility: every per-time-step span must start 16-byte aligned
+  const size_t sz = sizeof(R);
+  bool ok = aligned16(C) && aligned16(c) && aligned16(cur_x) && aligned16(cur_u) &&
+            (F == nullptr || aligned16(F)) && (!d->has_f || aligned16(f)) &&
+            (d->bounds_kind != 2 || (aligned16(u_lower) && aligned16(u_upper)));
+  ok = ok && ((size_t)d->B * d->m * sz) % 16 == 0 && ((size_t)d->B * d->n * sz) % 16 == 0;
+  a.bulk_ok = ok ? 1 : 0;
+  rc = (sizeof(R) == 4 ? e->step32 : e->step64)(a, smem, (cudaStream_t)stream);
+  if (rc == 0) g_launches.fetch_add(1);
+  return rc;
+}
+
+template <typename R>
+static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, const R* new_x,
+                     const R* new_u, const R* dx, const R* du, const R* dl_dx, R* dx_init, R* dC, R* dc,
+                     R* dF, R* df, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if (C == nullptr || c == nullptr || new_x == nullptr || new_u == nullptr || dx == nullptr ||
+      du == nullptr || dl_dx == nullptr || dx_init == nullptr || dC == nullptr || dc == nullptr)
+    return MPCB200_ERR_NULL_POINTER;
+  if (d->F_T > 0 && (F == nullptr || dF == nullptr)) return MPCB200_ERR_NULL_POINTER;
+  const Entry* e = find(d->n, d->m);
+  if (e == nullptr) return MPCB200_ERR_UNSUPPORTED_DIMS;
+  if (max_smem_optin() <= 0) return MPCB200_ERR_NO_DEVICE;
+  GradArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = d->B; a.T = d->T; a.F_T = d->F_T; a.has_df = df != nullptr;
+  a.C = C; a.c = c; a.F = F; a.new_x = new_x; a.new_u = new_u; a.dx = dx; a.du = du; a.dl_dx = dl_dx;
+  a.dx_init = dx_init; a.dC = dC; a.dc = dc; a.dF = dF; a.df = df;
+  rc = (sizeof(R) == 4 ? e->grad32 : e->grad64)(a, (cudaStream_t)stream);
+  if (rc == 0) g_launches.fetch_add(1);
+  return rc;
+}
+}  // namespace mpcb200
+
+using namespace mpcb200;
+
+extern "C" {
+
+int mpcb200_lqr_step_f32(const mpcb200_dims* dims, const mpcb200_params* params, const float* C,
+                         const float* c, const float* F, const float* f, const float* x_init,
+                         const float* cur_x, const float* cur_u, const float* u_lower,
+                         const float* u_upper, const uint8_t* u_zero_I, float* new_x, float* new_u,
+                         float* costs, float* full_du_norm, float* alphas, float* du_first, int32_t* qp_iters,
+                         uint8_t* free_mask, int32_t* status, float* Ks, float* ks, void* stream) {
+  return step_impl<float>(dims, params, C, c, F, f, x_init, cur_x, cur_u, u_lower, u_upper, u_zero_I,
+                          new_x, new_u, costs, full_du_norm, alphas, du_first, qp_iters, free_mask, status, Ks, ks,
+                          stream);
+}
+int mpcb200_lqr_step_f64(const mpcb200_dims* dims, const mpcb200_params* params, const double* C,
+                         const double* c, const double* F, const double* f, const double* x_init,
+                         const double* cur_x, const double* cur_u, const double* u_lower,
+                         const double* u_upper, const uint8_t* u_zero_I, double* new_x, double* new_u,
+                         double* costs, double* full_du_norm, double* alphas, double* du_first, int32_t* qp_iters,
+                         uint8_t* free_mask, int32_t* status, double* Ks, double* ks, void* stream) {
+  return step_impl<double>(dims, params, C, c, F, f, x_init, cur_x, cur_u, u_lower, u_upper, u_zero_I,
+                           new_x, new_u, costs, full_du_norm, alphas, du_first, qp_iters, free_mask, status, Ks, ks,
+                           stream);
+}
+int mpcb200_lqr_grad_f32(const mpcb200_dims* dims, const float* C, const float* c, const float* F,
+                         const float* new_x, const float* new_u, const float* dx, const float* du,
+                         const float* dl_dx, float* dx_init, float* dC, float* dc, float* dF, float* df,
+                         void* stream) {
+  return grad_impl<float>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, stream);
+}
+int mpcb200_lqr_grad_f64(const mpcb200_dims* dims, const double* C, const double* c, const double* F,
+                         const double* new_x, const double* new_u, const double* dx, const double* du,
+                         const double* dl_dx, double* dx_init, double* dC, double* dc, double* dF,
+                         double* df, void* stream) {
+  return grad_impl<double>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, stream);
+}
+
+int mpcb200_supported(int32_t n_state, int32_t n_ctrl) { return find(n_state, n_ctrl) != nullptr; }
+
+int mpcb200_supported_list(int32_t* out, int32_t cap) {
+  for (int i = 0; i < kTableLen && i < cap; ++i) {
+    out[2 * i] = kTable[i].n;
+    out[2 * i + 1] = kTable[i].m;
+  }
+  return kTableLen;
+}
+
+uint64_t mpcb200_launch_count(void) { return g_launches.load(); }
+
+size_t mpcb200_step_smem_bytes(const mpcb200_dims* dims, int32_t elem_size) {
+  if (dims == nullptr) return 0;
+  const Entry* e = find(dims->n, dims->m);
+  if (e == nullptr) return 0;
+  return elem_size == 8 ? e->smem64(dims->T) : e->smem32(dims->T);
+}
+
+int mpcb200_version(void) { return MPCB200_VERSION; }
+
+const char* mpcb200_strerror(int code) {
+  switch (code) {
+    case MPCB200_OK: return "ok";
+    case MPCB200_ERR_NULL_POINTER: return "a required pointer is NULL";
+    case MPCB200_ERR_BAD_DIMS: return "bad dimensions or option combination";
+    case MPCB200_ERR_UNSUPPORTED_DIMS: return "no kernel instance compiled for this (n_state, n_ctrl)";
+    case MPCB200_ERR_SMEM: return "problem does not fit shared memory (pass Ks/ks buffers for long horizons)";
+    case MPCB200_ERR_LAUNCH: return "CUDA launch failed";
+    case MPCB200_ERR_NO_DEVICE: return "no usable sm_100 device";
+    default: return "unknown error";
+  }
+}
+}  // extern "C"

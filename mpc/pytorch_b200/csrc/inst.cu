@@ -1,0 +1,30 @@
+// inst.cu - compiled once per (INST_N, INST_M) pair (see Makefile): explicit launchers for
+// the step and gradient kernels in float and double.
+#include "lqr_grad.cuh"
+#include "lqr_step.cuh"
+
+#ifndef INST_N
+#error "compile with -DINST_N=<n_state> -DINST_M=<n_ctrl>"
+#endif
+
+#define MPCB_CAT_(a, b, c, d) a##b##_##c##_##d
+#define MPCB_CAT(a, b, c, d) MPCB_CAT_(a, b, c, d)
+
+namespace mpcb200 {
+
+int MPCB_CAT(step_f32_, , INST_N, INST_M)(const StepArgs& a, int max_smem, cudaStream_t s) {
+  return launch_step<float, INST_N, INST_M>(a, max_smem, s);
+}
+int MPCB_CAT(step_f64_, , INST_N, INST_M)(const StepArgs& a, int max_smem, cudaStream_t s) {
+  return launch_step<double, INST_N, INST_M>(a, max_smem, s);
+}
+int MPCB_CAT(grad_f32_, , INST_N, INST_M)(const GradArgs& a, cudaStream_t s) {
+  return launch_grad<float, INST_N, INST_M>(a, s);
+}
+int MPCB_CAT(grad_f64_, , INST_N, INST_M)(const GradArgs& a, cudaStream_t s) {
+  return launch_grad<double, INST_N, INST_M>(a, s);
+}
+size_t MPCB_CAT(smem_f32_, , INST_N, INST_M)(int T) { return step_smem_query<float, INST_N, INST_M>(T); }
+size_t MPCB_CAT(smem_f64_, , INST_N, INST_M)(int T) { return step_smem_query<double, INST_N, INST_M>(T); }
+
+}  // namespace mpcb200

@@ -1,0 +1,717 @@
+// lqr_step.cuh - one box-constrained LQR step as ONE persistent-per-CTA kernel (sm_100a).
+//
+// Replaces the body of LQRStepFn.forward (reference mpc/lqr_step.py:277-309):
+//   c_back (:289-295), lqr_backward (:52-160) with pnqp (mpc/pnqp.py:5-82) or the
+//   u_zero_I masked solve (:100-127), and lqr_forward's rollout + line search (:164-261).
+//
+// Mapping (designed for B200, not translated from the reference's per-op loop):
+//  * P = n+m lanes own one problem; lane j owns COLUMN j of every p-wide matrix of that
+//    problem (Q_t, F_t, C_t) and, for j < n, column j of the value matrix V and of K_t.
+//    32/P problems share a warp, 4 consumer warps + 1 producer warp form a CTA.
+//  * the producer warp streams the per-time-step tiles C[t],F[t],c[t],f[t],x_bar[t],u_bar[t]
+//    (+ tensor bounds) of the CTA's W consecutive problems - contiguous in the reference's
+//    time-major layout - into a 3-stage shared-memory ring with 1-D bulk TMA
+//    (cp.async.bulk + mbarrier complete_tx); full/empty mbarriers pace it.  Shapes whose
+//    spans are not 16-byte aligned take a plain-load path in the same warp.
+//  * V (n x n, stored transposed), v, K_t and Q_xu live in a per-problem shared scratch and are re-read as
+//    broadcast vector loads; the m x m solve / pnqp runs redundantly on every lane of the
+//    problem from shuffled copies of Q_uu, q_u (registers only, no divergence inside a problem).
+//  * K_t,k_t for all t stay in shared memory between the backward sweep and the rollout;
+//    the rollout re-streams the tiles (L2 hits) and never round-trips gains through HBM
+//    (unless T is too long for shared memory, then a caller-provided Ks/ks buffer is used).
+//  * line search: per-problem alpha; a CTA repeats the rollout while any of its problems is
+//    worse and iterations remain - per problem this is exactly the reference's batch loop.
+#pragma once
+#include "common.cuh"
+
+namespace mpcb200 {
+
+struct StepArgs {
+  int B, T, F_T;
+  int has_f, bounds_kind, has_mask, has_delta, max_ls, pnqp_iters, do_rollout;
+  double u_lo, u_hi, delta_u, ls_decay;
+  const void *C, *c, *F, *f, *x_init, *cur_x, *cur_u, *u_lower, *u_upper;
+  const unsigned char* zero_mask;
+  void *new_x, *new_u, *costs, *full_du_norm, *alphas, *du_first;
+  int* qp_iters;
+  unsigned char* free_mask;
+  int* status;
+  void *Ks, *ks;
+  int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
+  int k_in_smem;  // gains of all T steps fit in shared memory
+};
+
+template <typename R, int N, int M>
+struct StepCfg {
+  static constexpr int P = N + M;
+  static_assert(P <= 32, "one problem must fit a warp");
+  static constexpr int LP = P;            // lanes per problem
+  static constexpr int PPW = 32 / LP;     // problems per warp
+  static constexpr int NW = 4;            // consumer warps
+  static constexpr int W = NW * PPW;      // problems per CTA (multiple of 4 -> 16B-aligned spans)
+  static constexpr int THREADS = (NW + 1) * 32;
+  static constexpr int S = 3;             // ring stages
+  static constexpr int VS = round_up(N, 4);
+  static constexpr int EA = 16 / (int)sizeof(R);
+  // stage tile offsets (elements); every sub-tile starts 16-byte aligned because W % 4 == 0
+  static constexpr int OFF_C = 0;
+  static constexpr int OFF_F = OFF_C + W * P * P;
+  static constexpr int OFF_c = OFF_F + W * N * P;
+  static constexpr int OFF_f = OFF_c + W * P;
+  static constexpr int OFF_x = OFF_f + W * N;
+  static constexpr int OFF_u = OFF_x + W * N;
+  static constexpr int OFF_lo = OFF_u + W * M;
+  static constexpr int OFF_hi = OFF_lo + W * M;
+  static constexpr int OFF_END = OFF_hi + W * M;
+  static constexpr int STAGE_BYTES = round_up(OFF_END * (int)sizeof(R) + round_up(W * M, 16), 128);
+  // per-problem scratch (elements)
+  static constexpr int SC_V = 0;                 // N x VS  value matrix
+  static constexpr int SC_v = SC_V + N * VS;     // VS      value vector
+  static constexpr int SC_K = SC_v + VS;         // M x VS (+ M) K_t,k_t exchange when gains are not smem resident
+  static constexpr int KT = M * VS + round_up(M, 4);  // elements per (problem, t) of the gain store
+  static constexpr int SC_Q = SC_K + KT;         // M x VS  Q_xu exchange (row a = Q[:n, n+a])
+  static constexpr int SC_X = SC_Q + M * VS;     // 2 x VS  rollout state exchange
+  static constexpr int SC_R = SC_X + 2 * VS;     // cost reduction
+  static constexpr int SC_RAW = SC_R + round_up(P, 4);
+  static constexpr int SCR = (SC_RAW % 32 == 0 || SC_RAW % 32 == 16) ? SC_RAW + 4 : SC_RAW;
+  static constexpr int HDR_BYTES = 256;          // 2*S mbarriers + 32 vote words
+  static size_t smem_bytes(int T, bool k_in_smem) {
+    size_t b = HDR_BYTES + (size_t)S * STAGE_BYTES + (size_t)W * SCR * sizeof(R);
+    if (k_in_smem) b += (size_t)W * T * KT * sizeof(R);
+    return b;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// pnqp for one problem, executed redundantly by every lane of the problem (registers only).
+// Control flow is what the reference takes for n_batch == 1 (mpc/pnqp.py:5-82).
+// ---------------------------------------------------------------------------------------------
+template <typename R, int M>
+MPCB_DEV void pnqp_lane(const R (&H)[M][M], const R (&q)[M], const R (&lo)[M], const R (&hi)[M],
+                        bool warm, R (&x)[M], Ldl<R, M>& fac, unsigned& fmask, int& iters,
+                        bool& conv, bool& badpiv, int max_iter) {
+  const R GAMMA = R(0.1);
+  auto obj = [&](const R(&z)[M]) {            // pnqp.py:11-12
+    R s = R(0);
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      R hz = R(0);
+#pragma unroll
+      for (int b = 0; b < M; ++b) hz += H[a][b] * z[b];
+      s += z[a] * (R(0.5) * hz + q[a]);
+    }
+    return s;
+  };
+  badpiv = false;
+  if (!warm) {                                 // pnqp.py:14-19
+    fac.factor(H);
+    badpiv = fac.bad;
+    R t[M];
+    fac.solve(q, t);
+#pragma unroll
+    for (int a = 0; a < M; ++a) x[a] = -t[a];
+  }
+#pragma unroll
+  for (int a = 0; a < M; ++a) x[a] = x[a] < lo[a] ? lo[a] : (x[a] > hi[a] ? hi[a] : x[a]);  // :23
+
+  for (int i = 0; i < max_iter; ++i) {
+    R g[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {              // :29
+      R s = q[a];
+#pragma unroll
+      for (int b = 0; b < M; ++b) s += H[a][b] * x[b];
+      g[a] = s;
+    }
+    fmask = 0u;
+#pragma unroll
+    for (int a = 0; a < M; ++a) {              // :32 exact equality with the assigned bound
+      const bool cl = ((x[a] == lo[a]) && (g[a] > R(0))) || ((x[a] == hi[a]) && (g[a] < R(0)));
+      if (!cl) fmask |= (1u << a);
+    }
+    R A[M][M], gm[M], dx[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {              // :44-48
+      const bool fa = (fmask >> a) & 1u;
+      gm[a] = fa ? g[a] : R(0);
+#pragma unroll
+      for (int b = 0; b < M; ++b) {
+        const bool fb = (fmask >> b) & 1u;
+        A[a][b] = (fa && fb) ? H[a][b] : R(0);
+      }
+      A[a][a] += R(1e-11);
+    }
+    fac.factor(A);
+    badpiv = badpiv || fac.bad;
+    fac.solve(gm, dx);                         // :53-54
+    R nrm2 = R(0);
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      dx[a] = -dx[a];
+      nrm2 += dx[a] * dx[a];
+    }
+    if (!(sqrt(nrm2) >= R(1e-4))) {            // :56-59
+      iters = i;
+      conv = true;
+      return;
+    }
+    R alpha = R(1), mx[M];
+    const R fx = obj(x);
+    int count = 0;
+    bool again;
+    do {                                       // :65-76 with n_batch == 1
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        const R v = x[a] + alpha * dx[a];
+        mx[a] = v < lo[a] ? lo[a] : (v > hi[a] ? hi[a] : v);
+      }
+      R den = R(0);
+#pragma unroll
+      for (int a = 0; a < M; ++a) den += g[a] * (x[a] - mx[a]);
+      const R arm = (fx - obj(mx)) / den;
+      again = arm <= GAMMA;                    // NaN compares false, like torch
+      if (again) alpha *= R(0.1);
+      ++count;
+    } while (again && count < 10);
+#pragma unroll
+    for (int a = 0; a < M; ++a) x[a] = mx[a];  // :78
+  }
+  iters = max_iter - 1;                        // :80-82
+  conv = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// producer warp: stream one (t) tile set of the CTA's problems into ring stage `tile % S`
+// ---------------------------------------------------------------------------------------------
+template <typename R, int N, int M>
+MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64_t* full,
+                            uint64_t* empty, volatile int* votes, int b0, int cnt, int lane) {
+  using K = StepCfg<R, N, M>;
+  constexpr int P = K::P;
+  constexpr uint32_t SZ = sizeof(R);
+  const R* gC = (const R*)a.C;
+  const R* gc = (const R*)a.c;
+  const R* gF = (const R*)a.F;
+  const R* gf = (const R*)a.f;
+  const R* gx = (const R*)a.cur_x;
+  const R* gu = (const R*)a.cur_u;
+  const R* glo = (const R*)a.u_lower;
+  const R* ghi = (const R*)a.u_upper;
+  const bool tail_ok = (cnt == K::W) || (((cnt * M * SZ) % 16 == 0) && ((cnt * N * SZ) % 16 == 0));
+  const bool bulk = a.bulk_ok && tail_ok;
+  const int T = a.T;
+  int tile = 0;
+
+  auto issue = [&](int t, bool fwd) {
+    const int s = tile % K::S;
+    const uint32_t ph = (uint32_t)(tile / K::S) & 1u;
+    mbar_wait(&empty[s], ph ^ 1u);
+    R* st = (R*)(stage_base + (size_t)s * K::STAGE_BYTES);
+    const size_t tb = (size_t)t * a.B + b0;
+    const bool needF = t < T - 1;
+    const bool needf = fwd && needF && a.has_f;
+    if (a.has_mask) {
+      unsigned char* mk = (unsigned char*)(st + K::OFF_END);
+      for (int i = lane; i < cnt * M; i += 32) mk[i] = a.zero_mask[tb * M + i];
+    }
+    if (bulk) {
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t bytes = (uint32_t)cnt * (P * P + P + N + M) * SZ;
+        if (needF) bytes += (uint32_t)cnt * N * P * SZ;
+        if (needf) bytes += (uint32_t)cnt * N * SZ;
+        if (a.bounds_kind == 2) bytes += 2u * cnt * M * SZ;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(st + K::OFF_C, gC + tb * P * P, (uint32_t)cnt * P * P * SZ, &full[s]);
+        if (needF) bulk_g2s(st + K::OFF_F, gF + tb * N * P, (uint32_t)cnt * N * P * SZ, &full[s]);
+        bulk_g2s(st + K::OFF_c, gc + tb * P, (uint32_t)cnt * P * SZ, &full[s]);
+        if (needf) bulk_g2s(st + K::OFF_f, gf + tb * N, (uint32_t)cnt * N * SZ, &full[s]);
+        bulk_g2s(st + K::OFF_x, gx + tb * N, (uint32_t)cnt * N * SZ, &full[s]);
+        bulk_g2s(st + K::OFF_u, gu + tb * M, (uint32_t)cnt * M * SZ, &full[s]);
+        if (a.bounds_kind == 2) {
+          bulk_g2s(st + K::OFF_lo, glo + tb * M, (uint32_t)cnt * M * SZ, &full[s]);
+          bulk_g2s(st + K::OFF_hi, ghi + tb * M, (uint32_t)cnt * M * SZ, &full[s]);
+        }
+      }
+    } else {
+      auto cp = [&](R* dst, const R* src, int nelem) {
+        for (int i = lane; i < nelem; i += 32) dst[i] = __ldg(src + i);
+      };
+      cp(st + K::OFF_C, gC + tb * P * P, cnt * P * P);
+      if (needF) cp(st + K::OFF_F, gF + tb * N * P, cnt * N * P);
+      cp(st + K::OFF_c, gc + tb * P, cnt * P);
+      if (needf) cp(st + K::OFF_f, gf + tb * N, cnt * N);
+      cp(st + K::OFF_x, gx + tb * N, cnt * N);
+      cp(st + K::OFF_u, gu + tb * M, cnt * M);
+      if (a.bounds_kind == 2) {
+        cp(st + K::OFF_lo, glo + tb * M, cnt * M);
+        cp(st + K::OFF_hi, ghi + tb * M, cnt * M);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    ++tile;
+  };
+
+  for (int t = T - 1; t >= 0; --t) issue(t, false);
+  if (a.do_rollout) {
+    for (int pass = 0;; ++pass) {
+      for (int t = 0; t < T; ++t) issue(t, true);
+      named_bar_sync(1, K::THREADS);
+      const int cont = votes[pass & 31];
+      if (!cont || pass + 1 >= a.max_ls) break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumer warps
+// ---------------------------------------------------------------------------------------------
+template <typename R, int N, int M>
+MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64_t* full,
+                            uint64_t* empty, volatile int* votes, R* scratch_all, R* kstore_all,
+                            int b0, int warp, int lane) {
+  using K = StepCfg<R, N, M>;
+  constexpr int P = K::P, LP = K::LP, PPW = K::PPW, VS = K::VS, EA = K::EA, KT = K::KT;
+  constexpr unsigned FULLM = (1u << M) - 1u;
+  const int T = a.T, B = a.B;
+  const bool writer_lane = lane < PPW * LP;
+  const int pi = writer_lane ? lane / LP : PPW - 1;
+  const int base = pi * LP;
+  const int j = writer_lane ? lane - base : LP - 1;
+  const int pw = warp * PPW + pi;
+  const int b = b0 + pw;
+  const bool valid = b < B;
+  const bool wr = writer_lane && valid;
+  const bool is_x = j < N;
+  const int ja = is_x ? 0 : j - N;      // control index of a u-column lane
+  const int jr = is_x ? j : N - 1;      // a valid F row for every lane
+
+  R* scr = scratch_all + (size_t)pw * K::SCR;
+  R* Vs = scr + K::SC_V;
+  R* vs = scr + K::SC_v;
+  R* Qx = scr + K::SC_Q;
+  R* xs = scr + K::SC_X;
+  R* red = scr + K::SC_R;
+  R* kst = a.k_in_smem ? kstore_all + (size_t)pw * T * KT : scr + K::SC_K;
+  R* gKs = (R*)a.Ks;
+  R* gks = (R*)a.ks;
+
+  const bool bounded = a.bounds_kind != 0;
+  const R s_lo = (R)a.u_lo, s_hi = (R)a.u_hi, s_du = (R)a.delta_u;
+  const R decay = (R)a.ls_decay;
+
+  int tile = 0;
+  unsigned status = 0u;
+  R oldcost_part = R(0);
+  R kprev[M];
+#pragma unroll
+  for (int q = 0; q < M; ++q) kprev[q] = R(0);
+
+  // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
+  for (int t = T - 1; t >= 0; --t) {
+    const int s = tile % K::S;
+    mbar_wait(&full[s], (uint32_t)(tile / K::S) & 1u);
+    const R* st = (const R*)(stage_base + (size_t)s * K::STAGE_BYTES);
+    const R* Cp = st + K::OFF_C + pw * P * P;
+    const R* Fp = st + K::OFF_F + pw * N * P;
+    const R* cp = st + K::OFF_c + pw * P;
+    const R* xp = st + K::OFF_x + pw * N;
+    const R* up = st + K::OFF_u + pw * M;
+    const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
+
+    // nominal point tau_bar = [x_bar; u_bar] replicated on every lane
+    R tb[P];
+    {
+      R tx[N], tu[M];
+      load_vec<R, N, vec_elems<R>(N)>(xp, tx);
+      load_vec<R, M, vec_elems<R>(M)>(up, tu);
+#pragma unroll
+      for (int i = 0; i < N; ++i) tb[i] = tx[i];
+#pragma unroll
+      for (int q = 0; q < M; ++q) tb[N + q] = tu[q];
+    }
+    // column j of C_t, and c_back_j = (C_t tau_bar)_j + c_j  (lqr_step.py:289-295)
+    R Qc[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) Qc[i] = Cp[i * P + j];
+    R Ct = R(0);
+#pragma unroll
+    for (int i = 0; i < P; ++i) Ct += Cp[j * P + i] * tb[i];
+    const R cj = cp[j];
+    const R tbj = is_x ? xp[j] : up[ja];
+    oldcost_part += tbj * (R(0.5) * Ct + cj);   // util.get_cost of the nominal trajectory (:169)
+    R qj = Ct + cj;
+
+    if (t < T - 1) {                            // Q = C + F'VF, q = c_back + F'v  (:66-70)
+      R Fcol[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) Fcol[k] = Fp[k * P + j];
+      R Wc[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) Wc[i] = R(0);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        R Vcol[VS];                      // Vs holds V transposed: row k of Vs == column k of V
+        load_vec<R, VS, EA>(Vs + k * VS, Vcol);
+#pragma unroll
+        for (int i = 0; i < N; ++i) Wc[i] += Vcol[i] * Fcol[k];
+      }
+      constexpr int FV = vec_elems<R>(N * P);
+#pragma unroll
+      for (int e0 = 0; e0 < N * P; e0 += FV) {
+        R tmp[FV];
+        VecLoad<R, FV>::ld(Fp + e0, tmp);
+#pragma unroll
+        for (int e = 0; e < FV; ++e) Qc[(e0 + e) % P] += tmp[e] * Wc[(e0 + e) / P];
+      }
+      R vv[VS];
+      load_vec<R, VS, EA>(vs, vv);
+#pragma unroll
+      for (int k = 0; k < N; ++k) qj += Fcol[k] * vv[k];
+    }
+
+    // replicate Q_uu, q_u on every lane of the problem
+    R Quu[M][M], qu[M];
+#pragma unroll
+    for (int p1 = 0; p1 < M; ++p1) {
+#pragma unroll
+      for (int p2 = 0; p2 < M; ++p2) Quu[p1][p2] = shfl(Qc[N + p1], base + N + p2);
+      qu[p1] = shfl(qj, base + N + p1);
+    }
+
+    R kk[M];
+    unsigned fm = FULLM;
+    int it = 0;
+    Ldl<R, M> fac;
+    if (bounded) {                               // (:129-148)
+      R lb[M], ub[M];
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        const R lo_abs = a.bounds_kind == 2 ? st[K::OFF_lo + pw * M + q] : s_lo;
+        const R hi_abs = a.bounds_kind == 2 ? st[K::OFF_hi + pw * M + q] : s_hi;
+        lb[q] = lo_abs - tb[N + q];
+        ub[q] = hi_abs - tb[N + q];
+        if (a.has_delta) {
+          if (lb[q] < -s_du) lb[q] = -s_du;
+          if (ub[q] > s_du) ub[q] = s_du;
+        }
+        kk[q] = kprev[q];
+      }
+      bool conv, badpiv;
+      pnqp_lane<R, M>(Quu, qu, lb, ub, t < T - 1, kk, fac, fm, it, conv, badpiv, a.pnqp_iters);
+      if (!conv) status |= 1u;
+      if (badpiv) status |= 4u;
+#pragma unroll
+      for (int q = 0; q < M; ++q) kprev[q] = kk[q];
+    } else {                                     // unconstrained (:84-94) or u_zero_I masked (:100-127)
+      if (a.has_mask) {
+        unsigned zm = 0u;
+#pragma unroll
+        for (int q = 0; q < M; ++q) zm |= (mk[q] ? 1u : 0u) << q;
+        fm = FULLM & ~zm;
+      }
+      R A[M][M], rhs[M], sol[M];
+#pragma unroll
+      for (int p1 = 0; p1 < M; ++p1) {
+        const bool f1 = (fm >> p1) & 1u;
+        rhs[p1] = f1 ? qu[p1] : R(0);
+#pragma unroll
+        for (int p2 = 0; p2 < M; ++p2) A[p1][p2] = (f1 && ((fm >> p2) & 1u)) ? Quu[p1][p2] : R(0);
+        if (!f1) A[p1][p1] += R(1e-8);
+      }
+      fac.factor(A);
+      if (fac.bad) status |= 4u;
+      fac.solve(rhs, sol);
+#pragma unroll
+      for (int q = 0; q < M; ++q) kk[q] = -sol[q];
+    }
+    // K[:, j] = -Hff^{-1} Qux_f[:, j]  (rows of clamped / masked controls are zero)
+    R Kc[M];
+    {
+      R rhs[M], sol[M];
+#pragma unroll
+      for (int q = 0; q < M; ++q) rhs[q] = ((fm >> q) & 1u) ? Qc[N + q] : R(0);
+      fac.solve(rhs, sol);
+#pragma unroll
+      for (int q = 0; q < M; ++q) Kc[q] = -sol[q];
+    }
+    R* Kt = a.k_in_smem ? kst + (size_t)t * KT : kst;
+    if (writer_lane) {
+      if (is_x) {
+#pragma unroll
+        for (int q = 0; q < M; ++q) Kt[q * VS + j] = Kc[q];
+      } else {                            // u lane: publish column n+ja of Q (rows < n) = Q_xu[:, ja]
+        R* dst = Qx + ja * VS;
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = Qc[i];
+      }
+    }
+    if (j == 0) {
+#pragma unroll
+      for (int q = 0; q < M; ++q) Kt[M * VS + q] = kk[q];
+    }
+    if (wr) {
+      if (gKs != nullptr) {
+        if (is_x) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) gKs[(((size_t)t * B + b) * M + q) * N + j] = Kc[q];
+        }
+        if (j == 0) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) gks[((size_t)t * B + b) * M + q] = kk[q];
+        }
+      }
+      if (a.qp_iters != nullptr && j == 0) a.qp_iters[(size_t)t * B + b] = it;
+      if (a.free_mask != nullptr && !is_x) a.free_mask[((size_t)t * B + b) * M + ja] = (fm >> ja) & 1u;
+    }
+    __syncwarp();
+
+    // V = Qxx + Qxu K + K'Qux + K'Quu K ; v = qx + Qxu k + K'qu + K'Quu k   (:155-158)
+    R G[M];
+#pragma unroll
+    for (int p1 = 0; p1 < M; ++p1) {
+      R sacc = Qc[N + p1];
+#pragma unroll
+      for (int p2 = 0; p2 < M; ++p2) sacc += Quu[p1][p2] * Kc[p2];
+      G[p1] = sacc;
+    }
+    R Vn[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) Vn[i] = Qc[i];
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+      R Qrow[VS], Krow[VS];
+      load_vec<R, VS, EA>(Qx + q * VS, Qrow);
+      load_vec<R, VS, EA>(Kt + q * VS, Krow);
+#pragma unroll
+      for (int i = 0; i < N; ++i) Vn[i] += Qrow[i] * Kc[q] + Krow[i] * G[q];
+    }
+    R vn = qj;
+#pragma unroll
+    for (int p1 = 0; p1 < M; ++p1) {
+      R sacc = qu[p1];
+#pragma unroll
+      for (int p2 = 0; p2 < M; ++p2) sacc += Quu[p1][p2] * kk[p2];
+      vn += Qx[p1 * VS + jr] * kk[p1] + Kc[p1] * sacc;
+    }
+    if (is_x && writer_lane) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) Vs[j * VS + i] = Vn[i];   // column j of V, stored as row j
+      vs[j] = vn;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    ++tile;
+  }
+
+  // nominal cost  (sum of the lanes' partial sums, fixed order)
+  if (writer_lane) red[j] = oldcost_part;
+  __syncwarp();
+  R oldcost = R(0);
+#pragma unroll
+  for (int i = 0; i < P; ++i) oldcost += red[i];
+  __syncwarp();
+
+  if (!a.do_rollout) {
+    if (wr && j == 0 && a.status != nullptr) a.status[b] = (int)status;
+    return;
+  }
+
+  // ======================= rollout + line search (lqr_step.py:164-261) =======================
+  const R* gx0 = (const R*)a.x_init;
+  R* gnx = (R*)a.new_x;
+  R* gnu = (R*)a.new_u;
+  R* gdu1 = (R*)a.du_first;
+  R alpha = R(1), fdn = R(0), cost = R(0);
+  bool worse = false;
+  for (int pass = 0;; ++pass) {
+    R xr[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) xr[i] = valid ? gx0[(size_t)b * N + i] : R(0);
+    R xown = valid ? gx0[(size_t)b * N + jr] : R(0);
+    R cpart = R(0), dun2 = R(0);
+    for (int t = 0; t < T; ++t) {
+      const int s = tile % K::S;
+      mbar_wait(&full[s], (uint32_t)(tile / K::S) & 1u);
+      const R* st = (const R*)(stage_base + (size_t)s * K::STAGE_BYTES);
+      const R* Cp = st + K::OFF_C + pw * P * P;
+      const R* Fp = st + K::OFF_F + pw * N * P;
+      const R* cp = st + K::OFF_c + pw * P;
+      const R* fp = st + K::OFF_f + pw * N;
+      const R* xp = st + K::OFF_x + pw * N;
+      const R* up = st + K::OFF_u + pw * M;
+      const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
+
+      R xb[N], ubar[M];
+      load_vec<R, N, vec_elems<R>(N)>(xp, xb);
+      load_vec<R, M, vec_elems<R>(M)>(up, ubar);
+      R u[M];
+      if (a.k_in_smem) {
+        const R* Kt = kst + (size_t)t * KT;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          R Krow[VS];
+          load_vec<R, VS, EA>(Kt + q * VS, Krow);
+          R sacc = R(0);
+#pragma unroll
+          for (int i = 0; i < N; ++i) sacc += Krow[i] * (xr[i] - xb[i]);
+          u[q] = (sacc + ubar[q]) + alpha * Kt[M * VS + q];      // (:192)
+        }
+      } else {
+        const R* Kg = gKs + ((size_t)t * B + (valid ? b : 0)) * M * N;
+        const R* kg = gks + ((size_t)t * B + (valid ? b : 0)) * M;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          R sacc = R(0);
+#pragma unroll
+          for (int i = 0; i < N; ++i) sacc += __ldcg(Kg + q * N + i) * (xr[i] - xb[i]);
+          u[q] = (sacc + ubar[q]) + alpha * __ldcg(kg + q);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        if (a.has_mask && mk[q]) u[q] = R(0);                     // (:197-198)
+        if (bounded) {                                           // (:200-213)
+          R lo = a.bounds_kind == 2 ? st[K::OFF_lo + pw * M + q] : s_lo;
+          R hi = a.bounds_kind == 2 ? st[K::OFF_hi + pw * M + q] : s_hi;
+          if (a.has_delta) {
+            const R l2 = ubar[q] - s_du, h2 = ubar[q] + s_du;
+            lo = l2 < lo ? lo : l2;
+            hi = h2 > hi ? hi : h2;
+          }
+          u[q] = u[q] < lo ? lo : (u[q] > hi ? hi : u[q]);
+        }
+        const R d = ubar[q] - u[q];
+        dun2 += d * d;
+      }
+      R tau[P];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tau[i] = xr[i];
+#pragma unroll
+      for (int q = 0; q < M; ++q) tau[N + q] = u[q];
+      R tj = xown;
+      if (!is_x) {
+#pragma unroll
+        for (int q = 0; q < M; ++q)
+          if (q == ja) tj = u[q];
+      }
+      R Ct = R(0);
+#pragma unroll
+      for (int i = 0; i < P; ++i) Ct += Cp[j * P + i] * tau[i];
+      cpart += tj * (R(0.5) * Ct + cp[j]);                        // (:232)
+      if (wr) {
+        if (is_x) {
+          gnx[((size_t)t * B + b) * N + j] = tj;
+        } else {
+          gnu[((size_t)t * B + b) * M + ja] = tj;
+          if (pass == 0 && gdu1 != nullptr) gdu1[((size_t)t * B + b) * M + ja] = up[ja] - tj;
+        }
+      }
+      if (t < T - 1) {                                            // (:217-222)
+        R xn = R(0);
+#pragma unroll
+        for (int i = 0; i < P; ++i) xn += Fp[jr * P + i] * tau[i];
+        if (a.has_f) xn += fp[jr];
+        R* xsb = xs + (t & 1) * VS;
+        if (is_x && writer_lane) xsb[j] = xn;
+        __syncwarp();
+        R xv[VS];
+        load_vec<R, VS, EA>(xsb, xv);
+#pragma unroll
+        for (int i = 0; i < N; ++i) xr[i] = xv[i];
+        xown = xn;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      ++tile;
+    }
+    if (writer_lane) red[j] = cpart;
+    __syncwarp();
+    cost = R(0);
+#pragma unroll
+    for (int i = 0; i < P; ++i) cost += red[i];
+    __syncwarp();
+    if (pass == 0) fdn = sqrt(dun2);                              // (:243-245)
+    worse = cost > oldcost;
+    const bool more = pass + 1 < a.max_ls;
+    if (worse) alpha *= decay;                                    // (:247)
+    if (wr && j == 0 && worse && more) votes[pass & 31] = 1;
+    if (warp == 0 && lane == 0) votes[(pass + 16) & 31] = 0;
+    named_bar_sync(1, K::THREADS);
+    const int cont = votes[pass & 31];
+    if (!cont || !more) break;
+  }
+  if (worse) alpha /= decay;                                      // (:252)
+  if (wr && j == 0) {
+    ((R*)a.costs)[b] = cost;
+    ((R*)a.full_du_norm)[b] = fdn;
+    ((R*)a.alphas)[b] = alpha;
+    if (!(cost - cost == R(0))) status |= 2u;
+    if (a.status != nullptr) a.status[b] = (int)status;
+  }
+}
+
+template <typename R, int N, int M>
+__global__ void __launch_bounds__(StepCfg<R, N, M>::THREADS)
+lqr_step_kernel(const StepArgs a) {
+  using K = StepCfg<R, N, M>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + K::S;
+  volatile int* votes = reinterpret_cast<volatile int*>(smem_raw + 128);
+  unsigned char* stage_base = smem_raw + K::HDR_BYTES;
+  R* scratch = reinterpret_cast<R*>(stage_base + (size_t)K::S * K::STAGE_BYTES);
+  R* kstore = scratch + (size_t)K::W * K::SCR;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * K::W;
+  const int cnt = min(K::W, a.B - b0);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < K::S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], K::NW);
+    }
+    mbar_fence_init();
+  }
+  if (tid < 32) votes[tid] = 0;
+  __syncthreads();
+  if (warp == K::NW) {
+    step_producer<R, N, M>(a, stage_base, full, empty, votes, b0, cnt, lane);
+  } else {
+    step_consumer<R, N, M>(a, stage_base, full, empty, votes, scratch, kstore, b0, warp, lane);
+  }
+}
+
+template <typename R, int N, int M>
+int launch_step(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
+  using K = StepCfg<R, N, M>;
+  StepArgs a = args;
+  size_t smem = K::smem_bytes(a.T, true);
+  a.k_in_smem = 1;
+  if (smem > (size_t)max_smem_optin) {
+    a.k_in_smem = 0;
+    smem = K::smem_bytes(a.T, false);
+    if (smem > (size_t)max_smem_optin) return 4;
+    if (a.do_rollout && (a.Ks == nullptr || a.ks == nullptr)) return 4;
+  }
+  auto kern = lqr_step_kernel<R, N, M>;
+  static int configured = 0;
+  if (configured < (int)smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) !=
+        cudaSuccess)
+      return 5;
+    configured = max_smem_optin;
+  }
+  const int grid = (a.B + K::W - 1) / K::W;
+  kern<<<grid, K::THREADS, smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 5;
+}
+
+template <typename R, int N, int M>
+size_t step_smem_query(int T) {
+  return StepCfg<R, N, M>::smem_bytes(T, true);
+}
+
+}  // namespace mpcb200

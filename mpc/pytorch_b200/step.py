@@ -1,0 +1,430 @@
+"""LQRStep: one box-constrained LQR step as a torch.autograd.Function over the C ABI.
+
+Mirrors the reference factory ``LQRStep(...)`` (mpc/lqr_step.py:22-38, 409): same
+keyword names, defaults, call signature ``(x_init, C, c, F, f)``, return arity and
+shapes, and the same gradient tuple ``(dx_init, dC, dc, dF, df)`` (:407).  The
+arithmetic runs in csrc/lqr_step.cuh and csrc/lqr_grad.cuh.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.nn import Module
+
+from . import _lib
+from ._lib import Dims, Params, MpcB200Error, check, ptr, stream_handle
+
+PNQP_MAX_ITER = 20  # reference passes n_iter=20 (mpc/lqr_step.py:137)
+
+
+def _is_empty(t):
+    return t is None or t.nelement() == 0
+
+
+def _dense(t, dtype=None):
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.detach().contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# padding to a compiled (n,m) instance (compatibility path for shapes without an exact kernel)
+# ----------------------------------------------------------------------------------------------
+_pairs_cache = None
+
+
+def _pick_instance(n, m):
+    global _pairs_cache
+    if _pairs_cache is None:
+        _pairs_cache = _lib.supported_pairs()
+    if (n, m) in _pairs_cache:
+        return n, m
+    cands = [(N + M, N, M) for (N, M) in _pairs_cache if N >= n and M >= m]
+    if not cands:
+        raise MpcB200Error(
+            f"(n_state={n}, n_ctrl={m}) exceeds every compiled kernel instance {_pairs_cache}; "
+            "add it to mpc/pytorch_b200/csrc/instances.def and rebuild")
+    _, N, M = min(cands)
+    return N, M
+
+
+class _Pad:
+    """Embeds an (n,m) problem in an (N,M) one: padded states are 0 with zero dynamics/cost;
+    padded controls get unit cost, zero linear term, no effect on the dynamics and bounds
+    [-1,1], so they stay at 0, free, and contribute nothing to any output."""
+
+    def __init__(self, n, m, N, M, device):
+        self.n, self.m, self.N, self.M = n, m, N, M
+        self.idx = torch.cat((torch.arange(n, device=device), N + torch.arange(m, device=device)))
+        self.active = (N, M) != (n, m)
+
+    def mat_pp(self, C):          # [..., p, p] -> [..., P, P]
+        out = C.new_zeros(*C.shape[:-2], self.N + self.M, self.N + self.M)
+        out[..., self.idx[:, None], self.idx[None, :]] = C
+        if self.M > self.m:
+            d = torch.arange(self.N + self.m, self.N + self.M, device=C.device)
+            out[..., d, d] = 1.0
+        return out
+
+    def vec_p(self, c):           # [..., p] -> [..., P]
+        out = c.new_zeros(*c.shape[:-1], self.N + self.M)
+        out[..., self.idx] = c
+        return out
+
+    def mat_np(self, F):          # [..., n, p] -> [..., N, P]
+        out = F.new_zeros(*F.shape[:-2], self.N, self.N + self.M)
+        out[..., : self.n, self.idx] = F
+        return out
+
+    def vec_n(self, x):
+        out = x.new_zeros(*x.shape[:-1], self.N)
+        out[..., : self.n] = x
+        return out
+
+    def vec_m(self, u, fill=0.0):
+        out = u.new_full((*u.shape[:-1], self.M), fill)
+        out[..., : self.m] = u
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# raw calls (dense CUDA tensors in, fresh CUDA tensors out)
+# ----------------------------------------------------------------------------------------------
+def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
+                 u_lower=None, u_upper=None, u_zero_I=None, delta_u=None,
+                 linesearch_decay=0.2, max_linesearch_iter=10, do_rollout=True,
+                 want_gains=False, want_stats=True, want_du_first=False):
+    """Run the step kernel.  Returns a dict of device tensors:
+    new_x,new_u,costs,full_du_norm,alphas (do_rollout) and, on request, Ks,ks,qp_iters,
+    free_mask,status."""
+    if not C.is_cuda:
+        raise MpcB200Error("mpc.pytorch_b200 runs on CUDA tensors only (no CPU fallback)")
+    dtype, dev = C.dtype, C.device
+    if dtype not in (torch.float32, torch.float64):
+        raise MpcB200Error(f"unsupported dtype {dtype}")
+    n, m = n_state, n_ctrl
+    B = C.shape[1]
+    N, M = _pick_instance(n, m)
+    pad = _Pad(n, m, N, M, dev)
+
+    C_, c_ = _dense(C, dtype), _dense(c, dtype)
+    F_ = _dense(F, dtype) if not _is_empty(F) else None
+    f_ = _dense(f, dtype) if not _is_empty(f) else None
+    x0_ = _dense(x_init, dtype) if x_init is not None else None
+    cx_, cu_ = _dense(cur_x, dtype), _dense(cur_u, dtype)
+    F_T = F_.shape[0] if F_ is not None else T - 1
+    bounds_kind = 0
+    lo_t = hi_t = None
+    s_lo = s_hi = 0.0
+    if u_lower is not None:
+        if isinstance(u_lower, float) and isinstance(u_upper, float) and not pad.active:
+            bounds_kind, s_lo, s_hi = 1, u_lower, u_upper
+        else:
+            bounds_kind = 2
+            lo_t = (torch.full((T, B, m), u_lower, dtype=dtype, device=dev)
+                    if isinstance(u_lower, float) else _dense(u_lower, dtype))
+            hi_t = (torch.full((T, B, m), u_upper, dtype=dtype, device=dev)
+                    if isinstance(u_upper, float) else _dense(u_upper, dtype))
+    zmask = None
+    if u_zero_I is not None:
+        zmask = (u_zero_I != 0).to(torch.uint8).contiguous()
+
+    if pad.active:
+        C_, c_ = pad.mat_pp(C_), pad.vec_p(c_)
+        F_ = pad.mat_np(F_) if F_ is not None else None
+        f_ = pad.vec_n(f_) if f_ is not None else None
+        x0_ = pad.vec_n(x0_) if x0_ is not None else None
+        cx_, cu_ = pad.vec_n(cx_), pad.vec_m(cu_)
+        if lo_t is not None:
+            lo_t, hi_t = pad.vec_m(lo_t, -1.0), pad.vec_m(hi_t, 1.0)
+        if zmask is not None:
+            zmask = pad.vec_m(zmask, 0)
+
+    out = {}
+    new_x = new_u = costs = fdn = alphas = None
+    if do_rollout:
+        new_x = torch.empty(T, B, N, dtype=dtype, device=dev)
+        new_u = torch.empty(T, B, M, dtype=dtype, device=dev)
+        costs = torch.empty(B, dtype=dtype, device=dev)
+        fdn = torch.empty(B, dtype=dtype, device=dev)
+        alphas = torch.empty(B, dtype=dtype, device=dev)
+    du_first = None
+    if do_rollout and want_du_first:
+        du_first = torch.empty(T, B, M, dtype=dtype, device=dev)
+    qp_iters = free_mask = status = None
+    if want_stats:
+        qp_iters = torch.zeros(T, B, dtype=torch.int32, device=dev) if bounds_kind else None
+        free_mask = torch.empty(T, B, M, dtype=torch.uint8, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+    Ks = ks = None
+    dims = Dims(B=B, T=T, n=N, m=M, F_T=F_T, has_f=int(f_ is not None), bounds_kind=bounds_kind,
+                has_zero_mask=int(zmask is not None), has_delta_u=int(delta_u is not None),
+                max_ls_iter=int(max_linesearch_iter), pnqp_max_iter=PNQP_MAX_ITER,
+                do_rollout=int(bool(do_rollout)))
+    L = _lib.lib()
+    need_gains = want_gains or not do_rollout
+    if not need_gains:
+        # long horizons do not fit shared memory: the kernel then keeps gains in a caller buffer
+        smem = L.mpcb200_step_smem_bytes(ctypes.byref(dims), C_.element_size())
+        need_gains = smem > 227 * 1024
+    if need_gains:
+        Ks = torch.empty(T, B, M, N, dtype=dtype, device=dev)
+        ks = torch.empty(T, B, M, dtype=dtype, device=dev)
+    params = Params(u_lo=float(s_lo), u_hi=float(s_hi),
+                    delta_u=float(delta_u) if delta_u is not None else 0.0,
+                    ls_decay=float(linesearch_decay))
+    fn = L.mpcb200_lqr_step_f32 if dtype == torch.float32 else L.mpcb200_lqr_step_f64
+    with torch.cuda.device(dev):
+        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr(C_), ptr(c_), ptr(F_), ptr(f_), ptr(x0_),
+                ptr(cx_), ptr(cu_), ptr(lo_t), ptr(hi_t), ptr(zmask), ptr(new_x), ptr(new_u),
+                ptr(costs), ptr(fdn), ptr(alphas), ptr(du_first), ptr(qp_iters), ptr(free_mask), ptr(status),
+                ptr(Ks), ptr(ks), stream_handle(dev))
+    check(rc, "mpcb200_lqr_step")
+    if do_rollout:
+        out.update(new_x=new_x[..., :n] if pad.active else new_x,
+                   new_u=new_u[..., :m] if pad.active else new_u,
+                   costs=costs, full_du_norm=fdn, alphas=alphas)
+        if du_first is not None:
+            out["du_first"] = du_first[..., :m] if pad.active else du_first
+    if Ks is not None:
+        out.update(Ks=Ks[..., :m, :n] if pad.active else Ks, ks=ks[..., :m] if pad.active else ks)
+    if want_stats:
+        out.update(qp_iters=qp_iters, free_mask=free_mask[..., :m] if pad.active else free_mask,
+                   status=status)
+    return out
+
+
+def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_df):
+    """Run the gradient-assembly kernel; returns (dx_init, dC, dc, dF, df|None)."""
+    dtype, dev = C.dtype, C.device
+    n, m = n_state, n_ctrl
+    B = C.shape[1]
+    N, M = _pick_instance(n, m)
+    pad = _Pad(n, m, N, M, dev)
+    C_, c_ = _dense(C, dtype), _dense(c, dtype)
+    F_ = _dense(F, dtype) if not _is_empty(F) else None
+    nx_, nu_ = _dense(new_x, dtype), _dense(new_u, dtype)
+    dx_, du_, r_ = _dense(dx, dtype), _dense(du, dtype), _dense(dl_dx, dtype)
+    F_T = F_.shape[0] if F_ is not None else 0
+    if pad.active:
+        C_, c_ = pad.mat_pp(C_), pad.vec_p(c_)
+        F_ = pad.mat_np(F_) if F_ is not None else None
+        nx_, nu_, dx_, du_, r_ = pad.vec_n(nx_), pad.vec_m(nu_), pad.vec_n(dx_), pad.vec_m(du_), pad.vec_n(r_)
+    P = N + M
+    dx_init = torch.empty(B, N, dtype=dtype, device=dev)
+    dC = torch.empty(T, B, P, P, dtype=dtype, device=dev)
+    dc = torch.empty(T, B, P, dtype=dtype, device=dev)
+    dF = torch.empty(F_T, B, N, P, dtype=dtype, device=dev) if F_ is not None else None
+    df = torch.empty(T - 1, B, N, dtype=dtype, device=dev) if want_df else None
+    dims = Dims(B=B, T=T, n=N, m=M, F_T=F_T if F_ is not None else T - 1, has_f=int(want_df),
+                bounds_kind=0, has_zero_mask=0, has_delta_u=0, max_ls_iter=1, pnqp_max_iter=1,
+                do_rollout=0)
+    L = _lib.lib()
+    fn = L.mpcb200_lqr_grad_f32 if dtype == torch.float32 else L.mpcb200_lqr_grad_f64
+    with torch.cuda.device(dev):
+        rc = fn(ctypes.byref(dims), ptr(C_), ptr(c_), ptr(F_), ptr(nx_), ptr(nu_), ptr(dx_), ptr(du_),
+                ptr(r_), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), stream_handle(dev))
+    check(rc, "mpcb200_lqr_grad")
+    if pad.active:
+        i = pad.idx
+        dx_init = dx_init[:, :n]
+        dC = dC[:, :, i[:, None], i[None, :]]
+        dc = dc[:, :, i]
+        dF = dF[:, :, :n][..., i] if dF is not None else None
+        df = df[..., :n] if df is not None else None
+    return dx_init, dC, dc, dF, df
+
+
+# ----------------------------------------------------------------------------------------------
+# split-mode rollout for nn.Module dynamics / costs (cannot run inside the kernel)
+# ----------------------------------------------------------------------------------------------
+def _bound_at(v, t):
+    return v if isinstance(v, float) else v[t]
+
+
+def _clamp_assign(x, lo, hi):
+    lo = torch.as_tensor(lo, dtype=x.dtype, device=x.device).expand_as(x)
+    hi = torch.as_tensor(hi, dtype=x.dtype, device=x.device).expand_as(x)
+    return torch.where(x > hi, hi, torch.where(x < lo, lo, x))
+
+
+def _stage_cost(true_cost, tau, t):
+    from .solver import QuadCost
+    if isinstance(true_cost, QuadCost):
+        Ct, ct = true_cost.C[t], true_cost.c[t]
+        return 0.5 * (tau * torch.einsum("bij,bj->bi", Ct, tau)).sum(1) + (tau * ct).sum(1)
+    return true_cost(tau)
+
+
+def _step_dynamics(true_dynamics, x, u, t):
+    from .solver import LinDx
+    if isinstance(true_dynamics, LinDx):
+        nx = torch.einsum("bij,bj->bi", true_dynamics.F[t], torch.cat((x, u), 1))
+        if not _is_empty(true_dynamics.f):
+            nx = nx + true_dynamics.f[t]
+        return nx
+    with torch.no_grad():
+        return true_dynamics(x, u)
+
+
+def rollout_split(T, x_init, cur_x, cur_u, Ks, ks, true_cost, true_dynamics,
+                  u_lower, u_upper, u_zero_I, delta_u, decay, max_iter):
+    """lqr_forward (reference mpc/lqr_step.py:164-261) with gains from the Riccati kernel and an
+    arbitrary true model, as batched torch ops on the device."""
+    B = x_init.shape[0]
+    with torch.no_grad():
+        old = 0
+        for t in range(T):
+            old = old + _stage_cost(true_cost, torch.cat((cur_x[t], cur_u[t]), 1), t)
+        alphas = torch.ones(B, dtype=x_init.dtype, device=x_init.device)
+        full_du_norm = None
+        cost = None
+        it = 0
+        while it < max_iter and (cost is None or bool((cost > old).any())):
+            xs, us = [x_init], []
+            cost = 0
+            for t in range(T):
+                u = torch.einsum("bij,bj->bi", Ks[t], xs[t] - cur_x[t]) + cur_u[t] \
+                    + alphas.unsqueeze(1) * ks[t]
+                if u_zero_I is not None:
+                    u = torch.where(u_zero_I[t].bool(), torch.zeros_like(u), u)
+                if u_lower is not None:
+                    lo, hi = _bound_at(u_lower, t), _bound_at(u_upper, t)
+                    if delta_u is not None:
+                        lo = torch.maximum(cur_u[t] - delta_u,
+                                           torch.as_tensor(lo, dtype=u.dtype, device=u.device).expand_as(u))
+                        hi = torch.minimum(cur_u[t] + delta_u,
+                                           torch.as_tensor(hi, dtype=u.dtype, device=u.device).expand_as(u))
+                    u = _clamp_assign(u, lo, hi)
+                us.append(u)
+                if t < T - 1:
+                    xs.append(_step_dynamics(true_dynamics, xs[t], u, t))
+                cost = cost + _stage_cost(true_cost, torch.cat((xs[t], u), 1), t)
+            new_x, new_u = torch.stack(xs), torch.stack(us)
+            if full_du_norm is None:
+                full_du_norm = (cur_u - new_u).transpose(1, 2).reshape(B, -1).norm(2, 1)
+            worse = cost > old
+            alphas = torch.where(worse, alphas * decay, alphas)
+            it += 1
+        alphas = torch.where(cost > old, alphas / decay, alphas)
+    return new_x, new_u, cost, full_du_norm, alphas
+
+
+def reference_full_du_norm(du_first):
+    """full_du_norm exactly as the reference forms it (mpc/lqr_step.py:244-245): the [T,B,m]
+    difference is transposed to [T,m,B] and VIEWED as [B, T*m] before the row norm, so for
+    B > 1 each entry mixes batch elements.  MPC's stop test / printed table depend on it."""
+    B = du_first.shape[1]
+    return du_first.transpose(1, 2).reshape(B, -1).norm(2, 1)
+
+
+def _same_storage(a, b):
+    if a is None or b is None:
+        return _is_empty(a) and _is_empty(b)
+    return a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride()
+
+
+# ----------------------------------------------------------------------------------------------
+# the factory (reference mpc/lqr_step.py:22-38)
+# ----------------------------------------------------------------------------------------------
+def LQRStep(n_state,
+            n_ctrl,
+            T,
+            u_lower=None,
+            u_upper=None,
+            u_zero_I=None,
+            delta_u=None,
+            linesearch_decay=0.2,
+            max_linesearch_iter=10,
+            true_cost=None,
+            true_dynamics=None,
+            delta_space=True,
+            current_x=None,
+            current_u=None,
+            verbose=0,
+            back_eps=1e-3,
+            no_op_forward=False):
+    """A single step of the box-constrained iLQR solver (drop-in for the reference factory).
+
+    Returns a callable ``(x_init, C, c, F, f=None)`` giving
+    ``(new_x[T,B,n], new_u[T,B,m], n_total_qp_iter (CPU float [1]), costs[B],
+    full_du_norm[B], mean_alphas (0-d))`` - or ``(current_x, current_u)`` when
+    ``no_op_forward`` - differentiable w.r.t. ``x_init, C, c, F, f``.
+    """
+    from .solver import QuadCost, LinDx
+
+    class LQRStepFn(Function):
+        @staticmethod
+        def forward(ctx, x_init, C, c, F, f=None):
+            if no_op_forward:                                   # reference :278-282
+                ctx.save_for_backward(x_init, C, c, F, f, current_x, current_u)
+                return current_x, current_u
+            assert delta_space                                  # reference :284,298
+            assert current_x is not None and current_u is not None
+            assert not (delta_u is not None and u_lower is None)   # reference :195
+
+            fused = (isinstance(true_cost, QuadCost) and isinstance(true_dynamics, LinDx)
+                     and _same_storage(true_cost.C, C) and _same_storage(true_cost.c, c)
+                     and _same_storage(true_dynamics.F, F)
+                     and (_same_storage(true_dynamics.f, f)
+                          or (_is_empty(true_dynamics.f) and _is_empty(f))))
+            if fused:
+                o = lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, current_x, current_u,
+                                 u_lower=u_lower, u_upper=u_upper, u_zero_I=u_zero_I, delta_u=delta_u,
+                                 linesearch_decay=linesearch_decay,
+                                 max_linesearch_iter=max_linesearch_iter, do_rollout=True,
+                                 want_du_first=True)
+                new_x, new_u = o["new_x"], o["new_u"]
+                costs, alphas = o["costs"], o["alphas"]
+                fdn = reference_full_du_norm(o["du_first"])
+            else:
+                assert true_cost is not None and true_dynamics is not None
+                o = lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, current_x, current_u,
+                                 u_lower=u_lower, u_upper=u_upper, u_zero_I=u_zero_I, delta_u=delta_u,
+                                 do_rollout=False)
+                new_x, new_u, costs, fdn, alphas = rollout_split(
+                    T, x_init.detach(), current_x.detach(), current_u.detach(), o["Ks"], o["ks"],
+                    true_cost, true_dynamics, u_lower, u_upper, u_zero_I, delta_u,
+                    linesearch_decay, max_linesearch_iter)
+            if u_lower is not None:
+                # reference: sum_t (1 + i_t) with one batched pnqp per step (:140)
+                n_qp = float((1 + o["qp_iters"].max(dim=1).values).sum().item())
+                if verbose >= 0 and bool((o["status"] & 1).any()):
+                    print("[WARNING] pnqp warning: Did not converge")   # reference pnqp.py:81
+            else:
+                n_qp = 0.0
+            ctx.save_for_backward(x_init, C, c, F, f, new_x, new_u)
+            return new_x, new_u, torch.Tensor([n_qp]), costs, fdn, alphas.mean()
+
+        @staticmethod
+        def backward(ctx, dl_dx, dl_du, temp=None, temp2=None, temp3=None, temp4=None):
+            x_init, C, c, F, f, new_x, new_u = ctx.saved_tensors
+            B = C.size(1)
+            if dl_dx is None:
+                dl_dx = torch.zeros_like(new_x)
+            if dl_du is None:
+                dl_du = torch.zeros_like(new_u)
+            r = torch.cat((dl_dx, dl_du), 2)                     # reference :316-320
+            if u_lower is None:
+                I = None
+            else:                                               # reference :325-326
+                I = (torch.abs(new_u - u_lower) <= 1e-8) | (torch.abs(new_u - u_upper) <= 1e-8)
+            zx = torch.zeros(T, B, n_state, dtype=C.dtype, device=C.device)
+            zu = torch.zeros(T, B, n_ctrl, dtype=C.dtype, device=C.device)
+            # nested MPC(lqr_iter=1, u_zero_I=I)(0, QuadCost(C,-r), LinDx(F,None)) (reference :328-340):
+            # one masked LQR step from the zero trajectory with the reference's default line search.
+            o = lqr_step_raw(n_state, n_ctrl, T, torch.zeros_like(x_init), C, -r, F, None, zx, zu,
+                             u_zero_I=I, linesearch_decay=0.2, max_linesearch_iter=10,
+                             do_rollout=True, want_stats=False)
+            want_df = not _is_empty(f)
+            dx_init, dC, dc, dF, df = lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u,
+                                                   o["new_x"], o["new_u"], dl_dx, want_df)
+            if dF is None:
+                dF = torch.zeros_like(F)
+            if df is None:                                       # reference :402 (empty tensor)
+                df = torch.zeros_like(f) if f is not None else None
+            return dx_init, dC, dc, dF, df
+
+    return LQRStepFn.apply

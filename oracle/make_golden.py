@@ -16,6 +16,7 @@ import io
 import os
 import sys
 import warnings
+import zlib
 
 import numpy as np
 import torch
@@ -94,7 +95,7 @@ def main():
                                     ("pnqp_f32_cold", 5, 3, torch.float32, False),
                                     ("pnqp_f64_n1", 7, 1, torch.float64, False),
                                     ("pnqp_f64_n100", 2, 100, torch.float64, False)]:
-        g = torch.Generator().manual_seed(hash(name) % 1000 + 17)
+        g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000 + 17)
         Lm = torch.randn(B, n, n, generator=g, dtype=torch.float64)
         H = (Lm @ Lm.transpose(1, 2) + 0.5 * torch.eye(n, dtype=torch.float64)).to(dtype)
         q = (2.0 * torch.randn(B, n, generator=g, dtype=torch.float64)).to(dtype)
@@ -224,6 +225,43 @@ def main():
     npz("tvlqr_notebook_f32", C=C, c=c, F=F, x_init=x0, u_lower=ul, u_upper=uu,
         x=xs, u=us, costs=costs, mean_costs=np.array(mean_costs),
         notebook_mean_costs=np.array(notebook))
+    # ---------------------------------------------------------------- cartpole iLQR (config 2 recipe, small)
+    # reference CartpoleDx needs matplotlib at import time (mpc/env_dx/cartpole.py:18-21): stub it.
+    import types
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib.pyplot"].style = types.SimpleNamespace(use=lambda *a, **k: None)
+    # the env module imports the package by its absolute name (`from mpc import util`):
+    # alias the reference under that name only while it is being imported.
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "mpc" or k.startswith("mpc.")}
+    sys.modules["mpc"] = sys.modules["ref_mpc"]
+    sys.modules["mpc.util"] = sys.modules["ref_mpc.util"]
+    import ref_mpc.env_dx.cartpole as rcart
+    for k in [k for k in sys.modules if k == "mpc" or k.startswith("mpc.")]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+    from tests.cartpole import Cartpole, initial_states
+    dxr, mine = rcart.CartpoleDx(), Cartpole()
+    B, T = 6, 12
+    x0 = initial_states(B, seed=0)
+    uu_ = torch.randn(B, 1)
+    close(mine(x0, uu_), dxr(x0, uu_), 1e-6, "cartpole.step")
+    q, p = dxr.get_true_obj()
+    q2, p2 = Cartpole.objective()
+    close(q2, q.data, 0, "cartpole.q"); close(p2, p.data, 0, "cartpole.p")
+    Q = torch.diag(q.data).unsqueeze(0).unsqueeze(0).repeat(T, B, 1, 1)
+    pp = p.data.unsqueeze(0).repeat(T, B, 1)
+    # (the reference's FINITE_DIFF path raises for batched Module dynamics; AUTO_DIFF is what its notebooks use)
+    for gm_name, gm in (("AUTO_DIFF", rmpc.GradMethods.AUTO_DIFF),):
+        with contextlib.redirect_stdout(io.StringIO()):
+            xs, us, costs = rmpc.MPC(5, 1, T, u_lower=dxr.lower, u_upper=dxr.upper, lqr_iter=8, verbose=-1,
+                                     exit_unconverged=False, detach_unconverged=False,
+                                     linesearch_decay=dxr.linesearch_decay,
+                                     max_linesearch_iter=dxr.max_linesearch_iter,
+                                     grad_method=gm, eps=1e-2)(x0, rmpc.QuadCost(Q, pp), dxr)
+        npz("cartpole_" + gm_name.lower() + "_f32", x_init=x0, Q=Q, p=pp, x=xs, u=us, costs=costs)
     print("all golden fixtures written; oracle == reference on every case")
 
 
