@@ -1,5 +1,6 @@
 // api.cu - the C ABI declared in include/mpcb200.h: argument checks, (n,m) dispatch, launch.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../../include/mpcb200.h"
@@ -120,6 +121,7 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
             (d->bounds_kind != 2 || (aligned16(u_lower) && aligned16(u_upper)));
   ok = ok && ((size_t)d->B * d->m * sz) % 16 == 0 && ((size_t)d->B * d->n * sz) % 16 == 0;
   a.bulk_ok = ok ? 1 : 0;
+  if (const char* dbg = std::getenv("MPCB200_DEBUG")) a.debug = std::atoi(dbg);
   rc = (sizeof(R) == 4 ? e->step32 : e->step64)(a, smem, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(1);
   return rc;

@@ -34,7 +34,22 @@ MPCB_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the
+// hint expires) instead of burning issue slots in a polling loop.
+MPCB_DEV bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 MPCB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // plain try_wait blocks in hardware for a bounded time; the suspend-hint form compiles to a
+  // NANOSLEEP polling loop (measured) whose wake-up granularity hurts a latency-bound consumer
   while (!mbar_try_wait(bar, parity)) {
   }
 }
@@ -104,11 +119,126 @@ MPCB_DEV void load_vec(const R* p, R (&out)[CNT]) {
 template <typename R>
 MPCB_DEV R shfl(R v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// ------------------------------------------------------------------ packed pairs (FFMA2 on sm_100)
+// Blackwell issues two fp32 FMAs per lane with one instruction (PTX fma.rn.f32x2, SASS FFMA2,
+// including a scalar-broadcast operand form).  Every lane-op is still an IEEE fma, so results are
+// those of scalar fmaf; the issue-slot count of the small dense products halves.
+template <typename R>
+struct P2 {
+  R x, y;
+};
+MPCB_DEV unsigned long long pack2(float x, float y) {
+  unsigned long long u;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(x), "f"(y));
+  return u;
+}
+MPCB_DEV P2<float> unpack2(unsigned long long u) {
+  P2<float> r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(u));
+  return r;
+}
+MPCB_DEV P2<float> fma2(P2<float> a, P2<float> b, P2<float> c) {   // a*b + c
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)), "l"(pack2(c.x, c.y)));
+  return unpack2(d);
+}
+MPCB_DEV P2<float> mul2(P2<float> a, P2<float> b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)));
+  return unpack2(d);
+}
+MPCB_DEV P2<double> fma2(P2<double> a, P2<double> b, P2<double> c) {
+  return {a.x * b.x + c.x, a.y * b.y + c.y};
+}
+MPCB_DEV P2<double> mul2(P2<double> a, P2<double> b) { return {a.x * b.x, a.y * b.y}; }
+
+// Fixed-length register vector stored as pairs (odd lengths carry one zero pad lane).
+template <typename R, int L>
+struct Vec {
+  static constexpr int NP = (L + 1) / 2;
+  P2<R> p[NP];
+  MPCB_DEV R get(int i) const { return (i & 1) ? p[i >> 1].y : p[i >> 1].x; }     // i: compile-time after unrolling
+  MPCB_DEV void set(int i, R v) {
+    if (i & 1) p[i >> 1].y = v;
+    else p[i >> 1].x = v;
+  }
+  MPCB_DEV void zero() {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) p[k] = {R(0), R(0)};
+  }
+  // this += a * s
+  MPCB_DEV void axpy(const Vec& a, R s) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) p[k] = fma2(a.p[k], P2<R>{s, s}, p[k]);
+  }
+  // sum_i this[i] * b[i]  (even/odd partial sums, then one add)
+  MPCB_DEV R dot(const Vec& b) const {
+    P2<R> acc = mul2(p[0], b.p[0]);
+#pragma unroll
+    for (int k = 1; k < NP; ++k) acc = fma2(p[k], b.p[k], acc);
+    return acc.x + acc.y;
+  }
+  // load L contiguous elements; V = vector width (elements) the address is aligned to
+  template <int V>
+  MPCB_DEV void load(const R* ptr) {
+    R tmp[NP * 2];
+    constexpr int LV = (L / V) * V;
+    if constexpr (LV > 0) {
+      R t2[LV > 0 ? LV : 1];
+      load_vec<R, (LV > 0 ? LV : V), V>(ptr, t2);
+#pragma unroll
+      for (int i = 0; i < LV; ++i) tmp[i] = t2[i];
+    }
+#pragma unroll
+    for (int i = LV; i < L; ++i) tmp[i] = ptr[i];
+    if constexpr (L & 1) tmp[L] = R(0);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) p[k] = {tmp[2 * k], tmp[2 * k + 1]};
+  }
+  // strided gather: element i from ptr[i * stride]
+  MPCB_DEV void gather(const R* ptr, int stride) {
+#pragma unroll
+    for (int i = 0; i < L; ++i) set(i, ptr[i * stride]);
+    if constexpr (L & 1) p[NP - 1].y = R(0);
+  }
+};
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int I>
+struct IC {
+  static constexpr int value = I;
+  MPCB_DEV constexpr operator int() const { return I; }
+};
+template <int B, int E, typename Fn>
+MPCB_DEV void static_for(Fn&& f) {
+  if constexpr (B < E) {
+    f(IC<B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+// widest vector width (elements) guaranteed for an address `base + off` when base is 16-byte
+// aligned and off is a multiple of `off_elems` elements
+template <typename R>
+__host__ __device__ constexpr int align_elems(int off_elems) {
+  return (off_elems * (int)sizeof(R)) % 16 == 0 ? 16 / (int)sizeof(R)
+         : (off_elems * (int)sizeof(R)) % 8 == 0 ? 8 / (int)sizeof(R)
+                                                 : 1;
+}
+
 // ------------------------------------------------------------------ M x M LDL^T (per lane, registers)
 // Factor a symmetric matrix A = L D L^T (unit lower L).  Only the lower triangle of A is read.
 // Masked (clamped) indices are presented by the caller as zero rows/cols with a tiny diagonal,
 // exactly how the reference builds H_ (mpc/pnqp.py:46-48) and Qt_uu_ (mpc/lqr_step.py:107-116):
 // they decouple, and a zero right-hand side gives an exactly zero solution component.
+// reciprocal: MUFU.RCP + one Newton step for float (<= 1 ulp, no slow-path call), IEEE for double
+MPCB_DEV float recip(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+MPCB_DEV double recip(double d) { return 1.0 / d; }
+
 template <typename R, int M>
 struct Ldl {
   R L[M][M];
@@ -125,7 +255,7 @@ struct Ldl {
       for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k] * d[k];
       bad = bad || !(dj > R(0));
       d[j] = dj;
-      dinv[j] = R(1) / dj;
+      dinv[j] = recip(dj);
 #pragma unroll
       for (int i = j + 1; i < M; ++i) {
         R s = A[i][j];

@@ -22,7 +22,12 @@
 //  * line search: per-problem alpha; a CTA repeats the rollout while any of its problems is
 //    worse and iterations remain - per problem this is exactly the reference's batch loop.
 #pragma once
+#include <cstdio>
 #include "common.cuh"
+
+#ifndef MPCB_STAGES
+#define MPCB_STAGES 3
+#endif
 
 namespace mpcb200 {
 
@@ -39,18 +44,39 @@ struct StepArgs {
   void *Ks, *ks;
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
+  int debug;      // developer experiments (env MPCB200_DEBUG): 1 = no data movement, 2 = no math
 };
 
 template <typename R, int N, int M>
 struct StepCfg {
   static constexpr int P = N + M;
   static_assert(P <= 32, "one problem must fit a warp");
-  static constexpr int LP = P;            // lanes per problem
-  static constexpr int PPW = 32 / LP;     // problems per warp
-  static constexpr int NW = 4;            // consumer warps
-  static constexpr int W = NW * PPW;      // problems per CTA (multiple of 4 -> 16B-aligned spans)
+  // columns per lane: 2 when the problem is wide enough (halves the shared-memory operand traffic
+  // per problem and doubles the independent FMA streams per lane), else 1.  Slot 0 of every lane
+  // must be a state column (LP <= N).
+  // Measured on B200 (config 3): CPL=2 is SLOWER (49 vs 41 us): with the whole batch resident in one
+  // wave the kernel time is (steps) x (per-step latency of a warp), and two columns per lane lengthen
+  // that chain.  Kept as a compile-time knob.
+#ifndef MPCB_CPL
+#define MPCB_CPL 1
+#endif
+  static constexpr int CPL = (MPCB_CPL == 2 && P >= 8 && (P + 1) / 2 <= N) ? 2 : 1;
+  static constexpr int LP = (P + CPL - 1) / CPL;   // lanes per problem
+  static constexpr int PPW = 32 / LP;               // problems per warp
+  // consumer warps per CTA: the smallest count whose per-time-step spans stay 16-byte aligned for every
+  // tensor (so the bulk-TMA path applies).  Small CTAs matter: 4096 problems are < 1 wave, and the
+  // kernel time is set by the most loaded SM, so the CTA granularity is the load-balance granularity.
+#ifndef MPCB_MAXNW
+#define MPCB_MAXNW 4
+#endif
+  static constexpr bool span_ok(int nw) {
+    return (nw * PPW * M * (int)sizeof(R)) % 16 == 0 && (nw * PPW * N * (int)sizeof(R)) % 16 == 0;
+  }
+  static constexpr int NW = (span_ok(1) && MPCB_MAXNW >= 1) ? 1 : (span_ok(2) && MPCB_MAXNW >= 2) ? 2 : 4;
+  static constexpr int W = NW * PPW;      // problems per CTA
+  static_assert(span_ok(NW), "CTA problem count must keep spans 16-byte aligned");
   static constexpr int THREADS = (NW + 1) * 32;
-  static constexpr int S = 3;             // ring stages
+  static constexpr int S = MPCB_STAGES;   // ring stages
   static constexpr int VS = round_up(N, 4);
   static constexpr int EA = 16 / (int)sizeof(R);
   // stage tile offsets (elements); every sub-tile starts 16-byte aligned because W % 4 == 0
@@ -200,11 +226,10 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
   const bool tail_ok = (cnt == K::W) || (((cnt * M * SZ) % 16 == 0) && ((cnt * N * SZ) % 16 == 0));
   const bool bulk = a.bulk_ok && tail_ok;
   const int T = a.T;
-  int tile = 0;
+  int s = 0;
+  uint32_t ph = 0;
 
   auto issue = [&](int t, bool fwd) {
-    const int s = tile % K::S;
-    const uint32_t ph = (uint32_t)(tile / K::S) & 1u;
     mbar_wait(&empty[s], ph ^ 1u);
     R* st = (R*)(stage_base + (size_t)s * K::STAGE_BYTES);
     const size_t tb = (size_t)t * a.B + b0;
@@ -214,7 +239,9 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
       unsigned char* mk = (unsigned char*)(st + K::OFF_END);
       for (int i = lane; i < cnt * M; i += 32) mk[i] = a.zero_mask[tb * M + i];
     }
-    if (bulk) {
+    if (a.debug & 1) {
+      if (lane == 0) mbar_arrive(&full[s]);
+    } else if (bulk) {
       __syncwarp();
       if (lane == 0) {
         uint32_t bytes = (uint32_t)cnt * (P * P + P + N + M) * SZ;
@@ -250,7 +277,7 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
     }
-    ++tile;
+    if (++s == K::S) { s = 0; ph ^= 1u; }
   };
 
   for (int t = T - 1; t >= 0; --t) issue(t, false);
@@ -265,15 +292,22 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
 }
 
 // ---------------------------------------------------------------------------------------------
-// consumer warps
+// consumer warps.  MODE (compile time): 0 plain (no bounds, no mask), 1 box (pnqp; optional
+// u_zero_I), 2 mask (u_zero_I only - the adjoint solve).
 // ---------------------------------------------------------------------------------------------
-template <typename R, int N, int M>
+enum { MODE_PLAIN = 0, MODE_BOX = 1, MODE_MASK = 2 };
+
+template <typename R, int N, int M, int MODE>
 MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64_t* full,
                             uint64_t* empty, volatile int* votes, R* scratch_all, R* kstore_all,
                             int b0, int warp, int lane) {
   using K = StepCfg<R, N, M>;
-  constexpr int P = K::P, LP = K::LP, PPW = K::PPW, VS = K::VS, EA = K::EA, KT = K::KT;
+  constexpr int P = K::P, LP = K::LP, PPW = K::PPW, CPL = K::CPL, VS = K::VS, EA = K::EA, KT = K::KT;
   constexpr unsigned FULLM = (1u << M) - 1u;
+  constexpr bool BOX = MODE == MODE_BOX;
+  constexpr int A_N = align_elems<R>(N), A_M = align_elems<R>(M);
+  constexpr int A_ROW = (P % 2 == 0) ? 2 : 1;   // row r*P of a per-problem tile (pair aligned for even P)
+  constexpr int A_2P = align_elems<R>(2 * P), A_NP = align_elems<R>(N * P);
   const int T = a.T, B = a.B;
   const bool writer_lane = lane < PPW * LP;
   const int pi = writer_lane ? lane / LP : PPW - 1;
@@ -283,9 +317,24 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   const int b = b0 + pw;
   const bool valid = b < B;
   const bool wr = writer_lane && valid;
-  const bool is_x = j < N;
-  const int ja = is_x ? 0 : j - N;      // control index of a u-column lane
-  const int jr = is_x ? j : N - 1;      // a valid F row for every lane
+
+  // the CPL columns this lane owns: col = j + s*LP (slot 0 is always a state column)
+  int cc[CPL], ua[CPL], fr[CPL];
+  bool isx[CPL], wsl[CPL];
+#pragma unroll
+  for (int sl = 0; sl < CPL; ++sl) {
+    const int col = j + sl * LP;
+    wsl[sl] = writer_lane && col < P;
+    cc[sl] = col < P ? col : P - 1;
+    isx[sl] = cc[sl] < N;
+    ua[sl] = isx[sl] ? 0 : cc[sl] - N;       // control index of a u column
+    fr[sl] = isx[sl] ? cc[sl] : N - 1;       // a valid row of F / V for every slot
+  }
+
+  // per-problem element offsets inside a stage (loop invariant)
+  const int oC = K::OFF_C + pw * P * P, oF = K::OFF_F + pw * N * P;
+  const int oc = K::OFF_c + pw * P, of_ = K::OFF_f + pw * N, ox = K::OFF_x + pw * N, ou = K::OFF_u + pw * M;
+  const int olo = K::OFF_lo + pw * M, ohi = K::OFF_hi + pw * M;
 
   R* scr = scratch_all + (size_t)pw * K::SCR;
   R* Vs = scr + K::SC_V;
@@ -297,106 +346,142 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   R* gKs = (R*)a.Ks;
   R* gks = (R*)a.ks;
 
-  const bool bounded = a.bounds_kind != 0;
   const R s_lo = (R)a.u_lo, s_hi = (R)a.u_hi, s_du = (R)a.delta_u;
   const R decay = (R)a.ls_decay;
+  const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
 
-  int tile = 0;
+  int stg = 0;
+  uint32_t ph = 0;
   unsigned status = 0u;
   R oldcost_part = R(0);
+#ifdef MPCB_TIMING
+  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tf[6] = {0, 0, 0, 0, 0, 0};
+  long long c0, c1;
+#define TICK(arr, i) { c1 = clock64(); arr[i] += c1 - c0; c0 = c1; }
+#else
+#define TICK(arr, i)
+#endif
   R kprev[M];
 #pragma unroll
   for (int q = 0; q < M; ++q) kprev[q] = R(0);
 
   // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
   for (int t = T - 1; t >= 0; --t) {
-    const int s = tile % K::S;
-    mbar_wait(&full[s], (uint32_t)(tile / K::S) & 1u);
-    const R* st = (const R*)(stage_base + (size_t)s * K::STAGE_BYTES);
-    const R* Cp = st + K::OFF_C + pw * P * P;
-    const R* Fp = st + K::OFF_F + pw * N * P;
-    const R* cp = st + K::OFF_c + pw * P;
-    const R* xp = st + K::OFF_x + pw * N;
-    const R* up = st + K::OFF_u + pw * M;
+#ifdef MPCB_TIMING
+    c0 = clock64();
+#endif
+    mbar_wait(&full[stg], ph);
+    TICK(tk, 0)
+    if (a.debug & 2) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stg]);
+      if (++stg == K::S) { stg = 0; ph ^= 1u; }
+      continue;
+    }
+    const R* st = (const R*)(stage_base + (size_t)stg * K::STAGE_BYTES);
     const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
 
     // nominal point tau_bar = [x_bar; u_bar] replicated on every lane
-    R tb[P];
+    Vec<R, P> tb;
     {
-      R tx[N], tu[M];
-      load_vec<R, N, vec_elems<R>(N)>(xp, tx);
-      load_vec<R, M, vec_elems<R>(M)>(up, tu);
+      Vec<R, N> tx;
+      Vec<R, M> tu;
+      tx.template load<A_N>(st + ox);
+      tu.template load<A_M>(st + ou);
 #pragma unroll
-      for (int i = 0; i < N; ++i) tb[i] = tx[i];
+      for (int i = 0; i < N; ++i) tb.set(i, tx.get(i));
 #pragma unroll
-      for (int q = 0; q < M; ++q) tb[N + q] = tu[q];
+      for (int q = 0; q < M; ++q) tb.set(N + q, tu.get(q));
+      if constexpr (P & 1) tb.p[Vec<R, P>::NP - 1].y = R(0);
     }
-    // column j of C_t, and c_back_j = (C_t tau_bar)_j + c_j  (lqr_step.py:289-295)
-    R Qc[P];
+    // owned columns of C_t; c_back = (C_t tau_bar) + c for the owned rows  (lqr_step.py:289-295)
+    Vec<R, P> Qc[CPL];
+    R qj[CPL];
 #pragma unroll
-    for (int i = 0; i < P; ++i) Qc[i] = Cp[i * P + j];
-    R Ct = R(0);
-#pragma unroll
-    for (int i = 0; i < P; ++i) Ct += Cp[j * P + i] * tb[i];
-    const R cj = cp[j];
-    const R tbj = is_x ? xp[j] : up[ja];
-    oldcost_part += tbj * (R(0.5) * Ct + cj);   // util.get_cost of the nominal trajectory (:169)
-    R qj = Ct + cj;
+    for (int sl = 0; sl < CPL; ++sl) {
+      Qc[sl].gather(st + oC + cc[sl], P);
+      Vec<R, P> Crow;
+      Crow.template load<A_ROW>(st + oC + cc[sl] * P);
+      const R Ct = Crow.dot(tb);
+      const R cj = st[oc + cc[sl]];
+      const R tbj = st[(isx[sl] ? ox : ou - N) + cc[sl]];
+      if (wsl[sl]) oldcost_part += tbj * (R(0.5) * Ct + cj);   // util.get_cost of the nominal trajectory (:169)
+      qj[sl] = Ct + cj;
+    }
 
+    TICK(tk, 1)
     if (t < T - 1) {                            // Q = C + F'VF, q = c_back + F'v  (:66-70)
-      R Fcol[N];
+      Vec<R, N> Fcol[CPL], Wc[CPL];
 #pragma unroll
-      for (int k = 0; k < N; ++k) Fcol[k] = Fp[k * P + j];
-      R Wc[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) Wc[i] = R(0);
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        R Vcol[VS];                      // Vs holds V transposed: row k of Vs == column k of V
-        load_vec<R, VS, EA>(Vs + k * VS, Vcol);
-#pragma unroll
-        for (int i = 0; i < N; ++i) Wc[i] += Vcol[i] * Fcol[k];
+      for (int sl = 0; sl < CPL; ++sl) {
+        Fcol[sl].gather(st + oF + cc[sl], P);
+        Wc[sl].zero();
       }
-      constexpr int FV = vec_elems<R>(N * P);
 #pragma unroll
-      for (int e0 = 0; e0 < N * P; e0 += FV) {
-        R tmp[FV];
-        VecLoad<R, FV>::ld(Fp + e0, tmp);
+      for (int k = 0; k < N; ++k) {             // W[:, c] = V F[:, c]; each V column load feeds CPL columns
+        Vec<R, N> Vcol;                         // Vs holds V transposed: row k of Vs == column k of V
+        Vcol.template load<EA>(Vs + k * VS);
 #pragma unroll
-        for (int e = 0; e < FV; ++e) Qc[(e0 + e) % P] += tmp[e] * Wc[(e0 + e) / P];
+        for (int sl = 0; sl < CPL; ++sl) Wc[sl].axpy(Vcol, Fcol[sl].get(k));
       }
-      R vv[VS];
-      load_vec<R, VS, EA>(vs, vv);
+      static_for<0, N>([&](auto kc) {           // Q[:, c] += F' W[:, c]; rows of F are contiguous
+        constexpr int k = decltype(kc)::value;
+        constexpr int AK = k % 2 == 0 ? A_2P : align_elems<R>(P);
+        Vec<R, P> Frow;
+        Frow.template load<(AK < A_NP ? AK : A_NP)>(st + oF + k * P);
 #pragma unroll
-      for (int k = 0; k < N; ++k) qj += Fcol[k] * vv[k];
+        for (int sl = 0; sl < CPL; ++sl) Qc[sl].axpy(Frow, Wc[sl].get(k));
+      });
+      Vec<R, N> vv;
+      vv.template load<EA>(vs);
+#pragma unroll
+      for (int sl = 0; sl < CPL; ++sl) qj[sl] += Fcol[sl].dot(vv);
     }
 
-    // replicate Q_uu, q_u on every lane of the problem
+    TICK(tk, 2)
+    // replicate Q_uu, q_u on every lane of the problem (column n+b2 lives in lane (n+b2)%LP, slot (n+b2)/LP)
     R Quu[M][M], qu[M];
 #pragma unroll
-    for (int p1 = 0; p1 < M; ++p1) {
+    for (int p2 = 0; p2 < M; ++p2) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int src = base + (N + p2) % LP;
 #pragma unroll
-      for (int p2 = 0; p2 < M; ++p2) Quu[p1][p2] = shfl(Qc[N + p1], base + N + p2);
-      qu[p1] = shfl(qj, base + N + p1);
+      for (int p1 = 0; p1 < M; ++p1) Quu[p1][p2] = shfl(Qc[(N + p2) / LP].get(N + p1), src);
+      qu[p2] = shfl(qj[(N + p2) / LP], src);
     }
 
+    TICK(tk, 3)
     R kk[M];
     unsigned fm = FULLM;
     int it = 0;
     Ldl<R, M> fac;
-    if (bounded) {                               // (:129-148)
+    if constexpr (BOX) {                         // (:129-148)
       R lb[M], ub[M];
 #pragma unroll
       for (int q = 0; q < M; ++q) {
-        const R lo_abs = a.bounds_kind == 2 ? st[K::OFF_lo + pw * M + q] : s_lo;
-        const R hi_abs = a.bounds_kind == 2 ? st[K::OFF_hi + pw * M + q] : s_hi;
-        lb[q] = lo_abs - tb[N + q];
-        ub[q] = hi_abs - tb[N + q];
+        const R lo_abs = a.bounds_kind == 2 ? st[olo + q] : s_lo;
+        const R hi_abs = a.bounds_kind == 2 ? st[ohi + q] : s_hi;
+        const R ubq = tb.get(N + q);
+        lb[q] = lo_abs - ubq;
+        ub[q] = hi_abs - ubq;
         if (a.has_delta) {
           if (lb[q] < -s_du) lb[q] = -s_du;
           if (ub[q] > s_du) ub[q] = s_du;
         }
         kk[q] = kprev[q];
+      }
+      if (!valid) {   // padding problems of a tail CTA compute on stale shared memory: give their
+                      // (data dependent) pnqp loop a trivial QP so they never become the slowest warp
+#pragma unroll
+        for (int p1 = 0; p1 < M; ++p1) {
+#pragma unroll
+          for (int p2 = 0; p2 < M; ++p2) Quu[p1][p2] = p1 == p2 ? R(1) : R(0);
+          qu[p1] = R(0);
+          lb[p1] = R(-1);
+          ub[p1] = R(1);
+          kk[p1] = R(0);
+        }
       }
       bool conv, badpiv;
       pnqp_lane<R, M>(Quu, qu, lb, ub, t < T - 1, kk, fac, fm, it, conv, badpiv, a.pnqp_iters);
@@ -405,7 +490,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
       for (int q = 0; q < M; ++q) kprev[q] = kk[q];
     } else {                                     // unconstrained (:84-94) or u_zero_I masked (:100-127)
-      if (a.has_mask) {
+      if constexpr (MODE == MODE_MASK) {
         unsigned zm = 0u;
 #pragma unroll
         for (int q = 0; q < M; ++q) zm |= (mk[q] ? 1u : 0u) << q;
@@ -426,25 +511,27 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
       for (int q = 0; q < M; ++q) kk[q] = -sol[q];
     }
-    // K[:, j] = -Hff^{-1} Qux_f[:, j]  (rows of clamped / masked controls are zero)
-    R Kc[M];
-    {
+    TICK(tk, 4)
+    // K[:, c] = -Hff^{-1} Qux_f[:, c] for the owned columns (rows of clamped / masked controls are zero)
+    R Kc[CPL][M];
+    R* Kt = a.k_in_smem ? kst + (size_t)t * KT : kst;
+#pragma unroll
+    for (int sl = 0; sl < CPL; ++sl) {
       R rhs[M], sol[M];
 #pragma unroll
-      for (int q = 0; q < M; ++q) rhs[q] = ((fm >> q) & 1u) ? Qc[N + q] : R(0);
+      for (int q = 0; q < M; ++q) rhs[q] = ((fm >> q) & 1u) ? Qc[sl].get(N + q) : R(0);
       fac.solve(rhs, sol);
 #pragma unroll
-      for (int q = 0; q < M; ++q) Kc[q] = -sol[q];
-    }
-    R* Kt = a.k_in_smem ? kst + (size_t)t * KT : kst;
-    if (writer_lane) {
-      if (is_x) {
+      for (int q = 0; q < M; ++q) Kc[sl][q] = -sol[q];
+      if (wsl[sl]) {
+        if (isx[sl]) {
 #pragma unroll
-        for (int q = 0; q < M; ++q) Kt[q * VS + j] = Kc[q];
-      } else {                            // u lane: publish column n+ja of Q (rows < n) = Q_xu[:, ja]
-        R* dst = Qx + ja * VS;
+          for (int q = 0; q < M; ++q) Kt[q * VS + cc[sl]] = Kc[sl][q];
+        } else {                          // u column: publish Q[:n, n+ua] = Q_xu[:, ua]
+          R* dst = Qx + ua[sl] * VS;
 #pragma unroll
-        for (int i = 0; i < N; ++i) dst[i] = Qc[i];
+          for (int i = 0; i < N; ++i) dst[i] = Qc[sl].get(i);
+        }
       }
     }
     if (j == 0) {
@@ -452,57 +539,76 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
       for (int q = 0; q < M; ++q) Kt[M * VS + q] = kk[q];
     }
     if (wr) {
+      const size_t tbo = (size_t)t * B + b;
       if (gKs != nullptr) {
-        if (is_x) {
 #pragma unroll
-          for (int q = 0; q < M; ++q) gKs[(((size_t)t * B + b) * M + q) * N + j] = Kc[q];
+        for (int sl = 0; sl < CPL; ++sl) {
+          if (wsl[sl] && isx[sl]) {
+#pragma unroll
+            for (int q = 0; q < M; ++q) gKs[(tbo * M + q) * N + cc[sl]] = Kc[sl][q];
+          }
         }
         if (j == 0) {
 #pragma unroll
-          for (int q = 0; q < M; ++q) gks[((size_t)t * B + b) * M + q] = kk[q];
+          for (int q = 0; q < M; ++q) gks[tbo * M + q] = kk[q];
         }
       }
-      if (a.qp_iters != nullptr && j == 0) a.qp_iters[(size_t)t * B + b] = it;
-      if (a.free_mask != nullptr && !is_x) a.free_mask[((size_t)t * B + b) * M + ja] = (fm >> ja) & 1u;
+      if (BOX && a.qp_iters != nullptr && j == 0) a.qp_iters[tbo] = it;
+      if (a.free_mask != nullptr) {
+#pragma unroll
+        for (int sl = 0; sl < CPL; ++sl)
+          if (wsl[sl] && !isx[sl]) a.free_mask[tbo * M + ua[sl]] = (fm >> ua[sl]) & 1u;
+      }
     }
     __syncwarp();
+    TICK(tk, 5)
 
     // V = Qxx + Qxu K + K'Qux + K'Quu K ; v = qx + Qxu k + K'qu + K'Quu k   (:155-158)
-    R G[M];
+    Vec<R, N> Vn[CPL];
+    R vn[CPL], G[CPL][M];
 #pragma unroll
-    for (int p1 = 0; p1 < M; ++p1) {
-      R sacc = Qc[N + p1];
+    for (int sl = 0; sl < CPL; ++sl) {
 #pragma unroll
-      for (int p2 = 0; p2 < M; ++p2) sacc += Quu[p1][p2] * Kc[p2];
-      G[p1] = sacc;
+      for (int p1 = 0; p1 < M; ++p1) {
+        R sacc = Qc[sl].get(N + p1);
+#pragma unroll
+        for (int p2 = 0; p2 < M; ++p2) sacc += Quu[p1][p2] * Kc[sl][p2];
+        G[sl][p1] = sacc;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) Vn[sl].set(i, Qc[sl].get(i));
+      if constexpr (N & 1) Vn[sl].p[Vec<R, N>::NP - 1].y = R(0);
+      vn[sl] = qj[sl];
     }
-    R Vn[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) Vn[i] = Qc[i];
 #pragma unroll
     for (int q = 0; q < M; ++q) {
-      R Qrow[VS], Krow[VS];
-      load_vec<R, VS, EA>(Qx + q * VS, Qrow);
-      load_vec<R, VS, EA>(Kt + q * VS, Krow);
+      Vec<R, N> Qrow, Krow;
+      Qrow.template load<EA>(Qx + q * VS);
+      Krow.template load<EA>(Kt + q * VS);
+      R sacc = qu[q];
 #pragma unroll
-      for (int i = 0; i < N; ++i) Vn[i] += Qrow[i] * Kc[q] + Krow[i] * G[q];
+      for (int p2 = 0; p2 < M; ++p2) sacc += Quu[q][p2] * kk[p2];
+#pragma unroll
+      for (int sl = 0; sl < CPL; ++sl) {
+        Vn[sl].axpy(Qrow, Kc[sl][q]);
+        Vn[sl].axpy(Krow, G[sl][q]);
+        vn[sl] += Qx[q * VS + fr[sl]] * kk[q] + Kc[sl][q] * sacc;
+      }
     }
-    R vn = qj;
 #pragma unroll
-    for (int p1 = 0; p1 < M; ++p1) {
-      R sacc = qu[p1];
+    for (int sl = 0; sl < CPL; ++sl) {
+      if (wsl[sl] && isx[sl]) {
+        R* dst = Vs + cc[sl] * VS;        // column c of V, stored as row c
 #pragma unroll
-      for (int p2 = 0; p2 < M; ++p2) sacc += Quu[p1][p2] * kk[p2];
-      vn += Qx[p1 * VS + jr] * kk[p1] + Kc[p1] * sacc;
+        for (int i = 0; i < N; ++i) dst[i] = Vn[sl].get(i);
+        vs[cc[sl]] = vn[sl];
+      }
     }
-    if (is_x && writer_lane) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) Vs[j * VS + i] = Vn[i];   // column j of V, stored as row j
-      vs[j] = vn;
-    }
+    TICK(tk, 6)
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-    ++tile;
+    if (lane == 0) mbar_arrive(&empty[stg]);
+    if (++stg == K::S) { stg = 0; ph ^= 1u; }
+    TICK(tk, 7)
   }
 
   // nominal cost  (sum of the lanes' partial sums, fixed order)
@@ -510,7 +616,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   __syncwarp();
   R oldcost = R(0);
 #pragma unroll
-  for (int i = 0; i < P; ++i) oldcost += red[i];
+  for (int i = 0; i < LP; ++i) oldcost += red[i];
   __syncwarp();
 
   if (!a.do_rollout) {
@@ -526,37 +632,44 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   R alpha = R(1), fdn = R(0), cost = R(0);
   bool worse = false;
   for (int pass = 0;; ++pass) {
-    R xr[N];
+    Vec<R, N> xr;
 #pragma unroll
-    for (int i = 0; i < N; ++i) xr[i] = valid ? gx0[(size_t)b * N + i] : R(0);
-    R xown = valid ? gx0[(size_t)b * N + jr] : R(0);
+    for (int i = 0; i < N; ++i) xr.set(i, valid ? gx0[(size_t)b * N + i] : R(0));
+    if constexpr (N & 1) xr.p[Vec<R, N>::NP - 1].y = R(0);
+    R xown[CPL];
+#pragma unroll
+    for (int sl = 0; sl < CPL; ++sl) xown[sl] = valid ? gx0[(size_t)b * N + fr[sl]] : R(0);
     R cpart = R(0), dun2 = R(0);
-    for (int t = 0; t < T; ++t) {
-      const int s = tile % K::S;
-      mbar_wait(&full[s], (uint32_t)(tile / K::S) & 1u);
-      const R* st = (const R*)(stage_base + (size_t)s * K::STAGE_BYTES);
-      const R* Cp = st + K::OFF_C + pw * P * P;
-      const R* Fp = st + K::OFF_F + pw * N * P;
-      const R* cp = st + K::OFF_c + pw * P;
-      const R* fp = st + K::OFF_f + pw * N;
-      const R* xp = st + K::OFF_x + pw * N;
-      const R* up = st + K::OFF_u + pw * M;
+    size_t orow = (size_t)b;                     // t*B + b
+    for (int t = 0; t < T; ++t, orow += (size_t)B) {
+#ifdef MPCB_TIMING
+      c0 = clock64();
+#endif
+      mbar_wait(&full[stg], ph);
+      TICK(tf, 0)
+      if (a.debug & 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stg]);
+        if (++stg == K::S) { stg = 0; ph ^= 1u; }
+        continue;
+      }
+      const R* st = (const R*)(stage_base + (size_t)stg * K::STAGE_BYTES);
       const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
 
-      R xb[N], ubar[M];
-      load_vec<R, N, vec_elems<R>(N)>(xp, xb);
-      load_vec<R, M, vec_elems<R>(M)>(up, ubar);
+      Vec<R, N> xb, dxv;
+      Vec<R, M> ubar;
+      xb.template load<A_N>(st + ox);
+      ubar.template load<A_M>(st + ou);
+#pragma unroll
+      for (int k2 = 0; k2 < Vec<R, N>::NP; ++k2) dxv.p[k2] = fma2(xb.p[k2], P2<R>{R(-1), R(-1)}, xr.p[k2]);
       R u[M];
       if (a.k_in_smem) {
         const R* Kt = kst + (size_t)t * KT;
 #pragma unroll
         for (int q = 0; q < M; ++q) {
-          R Krow[VS];
-          load_vec<R, VS, EA>(Kt + q * VS, Krow);
-          R sacc = R(0);
-#pragma unroll
-          for (int i = 0; i < N; ++i) sacc += Krow[i] * (xr[i] - xb[i]);
-          u[q] = (sacc + ubar[q]) + alpha * Kt[M * VS + q];      // (:192)
+          Vec<R, N> Krow;
+          Krow.template load<EA>(Kt + q * VS);
+          u[q] = (Krow.dot(dxv) + ubar.get(q)) + alpha * Kt[M * VS + q];      // (:192)
         }
       } else {
         const R* Kg = gKs + ((size_t)t * B + (valid ? b : 0)) * M * N;
@@ -565,72 +678,88 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
         for (int q = 0; q < M; ++q) {
           R sacc = R(0);
 #pragma unroll
-          for (int i = 0; i < N; ++i) sacc += __ldcg(Kg + q * N + i) * (xr[i] - xb[i]);
-          u[q] = (sacc + ubar[q]) + alpha * __ldcg(kg + q);
+          for (int i = 0; i < N; ++i) sacc += __ldcg(Kg + q * N + i) * dxv.get(i);
+          u[q] = (sacc + ubar.get(q)) + alpha * __ldcg(kg + q);
         }
       }
 #pragma unroll
       for (int q = 0; q < M; ++q) {
-        if (a.has_mask && mk[q]) u[q] = R(0);                     // (:197-198)
-        if (bounded) {                                           // (:200-213)
-          R lo = a.bounds_kind == 2 ? st[K::OFF_lo + pw * M + q] : s_lo;
-          R hi = a.bounds_kind == 2 ? st[K::OFF_hi + pw * M + q] : s_hi;
+        if constexpr (MODE != MODE_PLAIN) {
+          if (has_mask && mk[q]) u[q] = R(0);                     // (:197-198)
+        }
+        if constexpr (BOX) {                                      // (:200-213)
+          R lo = a.bounds_kind == 2 ? st[olo + q] : s_lo;
+          R hi = a.bounds_kind == 2 ? st[ohi + q] : s_hi;
           if (a.has_delta) {
-            const R l2 = ubar[q] - s_du, h2 = ubar[q] + s_du;
+            const R l2 = ubar.get(q) - s_du, h2 = ubar.get(q) + s_du;
             lo = l2 < lo ? lo : l2;
             hi = h2 > hi ? hi : h2;
           }
           u[q] = u[q] < lo ? lo : (u[q] > hi ? hi : u[q]);
         }
-        const R d = ubar[q] - u[q];
+        const R d = ubar.get(q) - u[q];
         dun2 += d * d;
       }
-      R tau[P];
+      TICK(tf, 1)
+      Vec<R, P> tau;
 #pragma unroll
-      for (int i = 0; i < N; ++i) tau[i] = xr[i];
+      for (int i = 0; i < N; ++i) tau.set(i, xr.get(i));
 #pragma unroll
-      for (int q = 0; q < M; ++q) tau[N + q] = u[q];
-      R tj = xown;
-      if (!is_x) {
+      for (int q = 0; q < M; ++q) tau.set(N + q, u[q]);
+      if constexpr (P & 1) tau.p[Vec<R, P>::NP - 1].y = R(0);
+
+      R xn[CPL];
 #pragma unroll
-        for (int q = 0; q < M; ++q)
-          if (q == ja) tj = u[q];
-      }
-      R Ct = R(0);
+      for (int sl = 0; sl < CPL; ++sl) {
+        R tj = xown[sl];
+        if (!isx[sl]) {
 #pragma unroll
-      for (int i = 0; i < P; ++i) Ct += Cp[j * P + i] * tau[i];
-      cpart += tj * (R(0.5) * Ct + cp[j]);                        // (:232)
-      if (wr) {
-        if (is_x) {
-          gnx[((size_t)t * B + b) * N + j] = tj;
-        } else {
-          gnu[((size_t)t * B + b) * M + ja] = tj;
-          if (pass == 0 && gdu1 != nullptr) gdu1[((size_t)t * B + b) * M + ja] = up[ja] - tj;
+          for (int q = 0; q < M; ++q)
+            if (q == ua[sl]) tj = u[q];
+        }
+        Vec<R, P> Crow;
+        Crow.template load<A_ROW>(st + oC + cc[sl] * P);
+        const R Ct = Crow.dot(tau);
+        if (wsl[sl]) cpart += tj * (R(0.5) * Ct + st[oc + cc[sl]]);           // (:232)
+        if (wr && wsl[sl]) {
+          if (isx[sl]) {
+            gnx[orow * N + cc[sl]] = tj;
+          } else {
+            gnu[orow * M + ua[sl]] = tj;
+            if (pass == 0 && gdu1 != nullptr) gdu1[orow * M + ua[sl]] = st[ou + ua[sl]] - tj;
+          }
+        }
+        xn[sl] = R(0);
+        if (t < T - 1) {                                          // (:217-222)
+          Vec<R, P> Frow;
+          Frow.template load<A_ROW>(st + oF + fr[sl] * P);
+          xn[sl] = Frow.dot(tau);
+          if (a.has_f) xn[sl] += st[of_ + fr[sl]];
         }
       }
-      if (t < T - 1) {                                            // (:217-222)
-        R xn = R(0);
-#pragma unroll
-        for (int i = 0; i < P; ++i) xn += Fp[jr * P + i] * tau[i];
-        if (a.has_f) xn += fp[jr];
+      TICK(tf, 2)
+      if (t < T - 1) {
         R* xsb = xs + (t & 1) * VS;
-        if (is_x && writer_lane) xsb[j] = xn;
-        __syncwarp();
-        R xv[VS];
-        load_vec<R, VS, EA>(xsb, xv);
 #pragma unroll
-        for (int i = 0; i < N; ++i) xr[i] = xv[i];
-        xown = xn;
+        for (int sl = 0; sl < CPL; ++sl) {
+          if (wsl[sl] && isx[sl]) xsb[cc[sl]] = xn[sl];
+          xown[sl] = xn[sl];
+        }
+        __syncwarp();
+        xr.template load<EA>(xsb);
+        if constexpr (N & 1) xr.p[Vec<R, N>::NP - 1].y = R(0);
       }
+      TICK(tf, 3)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-      ++tile;
+      if (lane == 0) mbar_arrive(&empty[stg]);
+      if (++stg == K::S) { stg = 0; ph ^= 1u; }
+      TICK(tf, 4)
     }
     if (writer_lane) red[j] = cpart;
     __syncwarp();
     cost = R(0);
 #pragma unroll
-    for (int i = 0; i < P; ++i) cost += red[i];
+    for (int i = 0; i < LP; ++i) cost += red[i];
     __syncwarp();
     if (pass == 0) fdn = sqrt(dun2);                              // (:243-245)
     worse = cost > oldcost;
@@ -642,6 +771,12 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
     const int cont = votes[pass & 31];
     if (!cont || !more) break;
   }
+#ifdef MPCB_TIMING
+  if (lane == 0 && (blockIdx.x % 97) == 0 && warp == 0)
+    printf("cta %d T=%d bwd/step: wait %lld pre %lld WQ %lld shfl %lld solve %lld Kexch %lld Vupd %lld rel %lld | fwd/step: wait %lld u %lld rows %lld xchg %lld rel %lld\n",
+           blockIdx.x, T, tk[0] / T, tk[1] / T, tk[2] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T, tk[7] / T,
+           tf[0] / T, tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
+#endif
   if (worse) alpha /= decay;                                      // (:252)
   if (wr && j == 0) {
     ((R*)a.costs)[b] = cost;
@@ -652,7 +787,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   }
 }
 
-template <typename R, int N, int M>
+template <typename R, int N, int M, int MODE>
 __global__ void __launch_bounds__(StepCfg<R, N, M>::THREADS)
 lqr_step_kernel(const StepArgs a) {
   using K = StepCfg<R, N, M>;
@@ -676,16 +811,26 @@ lqr_step_kernel(const StepArgs a) {
     mbar_fence_init();
   }
   if (tid < 32) votes[tid] = 0;
+  if (a.debug & 1) {   // experiment: no data movement -> deterministic (identity-like) tiles
+    R* stf = reinterpret_cast<R*>(stage_base);
+    for (int i = tid; i < K::S * K::STAGE_BYTES / (int)sizeof(R); i += K::THREADS) stf[i] = R(0);
+    __syncthreads();
+    for (int s = 0; s < K::S; ++s)
+      for (int i = tid; i < K::W * K::P; i += K::THREADS) {
+        R* Ct = reinterpret_cast<R*>(stage_base + (size_t)s * K::STAGE_BYTES) + K::OFF_C;
+        Ct[(i / K::P) * K::P * K::P + (i % K::P) * (K::P + 1)] = R(1);   // C = I
+      }
+  }
   __syncthreads();
   if (warp == K::NW) {
     step_producer<R, N, M>(a, stage_base, full, empty, votes, b0, cnt, lane);
   } else {
-    step_consumer<R, N, M>(a, stage_base, full, empty, votes, scratch, kstore, b0, warp, lane);
+    step_consumer<R, N, M, MODE>(a, stage_base, full, empty, votes, scratch, kstore, b0, warp, lane);
   }
 }
 
-template <typename R, int N, int M>
-int launch_step(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
+template <typename R, int N, int M, int MODE>
+int launch_step_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
   using K = StepCfg<R, N, M>;
   StepArgs a = args;
   size_t smem = K::smem_bytes(a.T, true);
@@ -696,7 +841,7 @@ int launch_step(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
     if (smem > (size_t)max_smem_optin) return 4;
     if (a.do_rollout && (a.Ks == nullptr || a.ks == nullptr)) return 4;
   }
-  auto kern = lqr_step_kernel<R, N, M>;
+  auto kern = lqr_step_kernel<R, N, M, MODE>;
   static int configured = 0;
   if (configured < (int)smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) !=
@@ -707,6 +852,13 @@ int launch_step(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
   const int grid = (a.B + K::W - 1) / K::W;
   kern<<<grid, K::THREADS, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 5;
+}
+
+template <typename R, int N, int M>
+int launch_step(const StepArgs& a, int max_smem_optin, cudaStream_t stream) {
+  if (a.bounds_kind != 0) return launch_step_mode<R, N, M, MODE_BOX>(a, max_smem_optin, stream);
+  if (a.has_mask) return launch_step_mode<R, N, M, MODE_MASK>(a, max_smem_optin, stream);
+  return launch_step_mode<R, N, M, MODE_PLAIN>(a, max_smem_optin, stream);
 }
 
 template <typename R, int N, int M>
