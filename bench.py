@@ -227,7 +227,8 @@ def main():
         sampler.start()
     # pre-heat (untimed, before the W warm-up steps): ~0.7 s of the same launches so that the
     # nvidia-smi samples are taken with the SMs at their loaded clocks
-    t_end = time.perf_counter() + 0.7
+    preheat = float(os.environ.get("BENCH_PREHEAT_S", "0.7"))   # set 0 under ncu (every launch is replayed)
+    t_end = time.perf_counter() + preheat
     i = 0
     while time.perf_counter() < t_end:
         for _ in range(50):
@@ -314,7 +315,7 @@ def main():
                      "bytes_per_solve": bps},
     })
     out["config"]["l2_policy"] = f"rotating {N_SETS} input sets ({N_SETS * bps * B / 1e6:.0f} MB > 126 MB L2)"
-    out["config"]["preheat_s"] = 0.7
+    out["config"]["preheat_s"] = preheat
     if world == 1:
         val, _, cores, sample = cpu_reference_arm(40, 2)
         out["cpu_baseline"] = {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample}

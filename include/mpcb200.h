@@ -118,20 +118,23 @@ int mpcb200_lqr_step_f64(const mpcb200_dims* dims, const mpcb200_params* params,
  *   df = -dlam[1:], dx_init = -dlam[0].
  * r = [dl_dx; dl_du] enters only through r_x.  dF has F_T slices (slice T-1, if present, is zeroed).
  * df may be NULL (reference returns an empty tensor when f is empty).
+ * workspace: optional device buffer of 2*T*B*n elements (lambda_t, dlambda_t).  With it the
+ * call runs as two kernels (sequential costates, then fully parallel outer products - the fast
+ * path); with NULL it runs as one fused kernel.  Results are identical.
  */
 int mpcb200_lqr_grad_f32(const mpcb200_dims* dims,
                          const float* C, const float* c, const float* F,
                          const float* new_x, const float* new_u,
                          const float* dx, const float* du, const float* dl_dx,
                          float* dx_init, float* dC, float* dc, float* dF, float* df,
-                         void* stream);
+                         void* workspace, void* stream);
 
 int mpcb200_lqr_grad_f64(const mpcb200_dims* dims,
                          const double* C, const double* c, const double* F,
                          const double* new_x, const double* new_u,
                          const double* dx, const double* du, const double* dl_dx,
                          double* dx_init, double* dC, double* dc, double* dF, double* df,
-                         void* stream);
+                         void* workspace, void* stream);
 
 /* 1 if a kernel instance for (n_state, n_ctrl) is compiled in, else 0. */
 int mpcb200_supported(int32_t n_state, int32_t n_ctrl);

@@ -53,7 +53,7 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = step_args
         fn.restype = ctypes.c_int
-    grad_args = [ctypes.POINTER(Dims)] + [vp] * 14
+    grad_args = [ctypes.POINTER(Dims)] + [vp] * 15
     for name in ("mpcb200_lqr_grad_f32", "mpcb200_lqr_grad_f64"):
         fn = getattr(L, name)
         fn.argtypes = grad_args

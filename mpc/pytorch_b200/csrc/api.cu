@@ -130,7 +130,7 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
 template <typename R>
 static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, const R* new_x,
                      const R* new_u, const R* dx, const R* du, const R* dl_dx, R* dx_init, R* dC, R* dc,
-                     R* dF, R* df, void* stream) {
+                     R* dF, R* df, void* workspace, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   if (C == nullptr || c == nullptr || new_x == nullptr || new_u == nullptr || dx == nullptr ||
@@ -144,9 +144,9 @@ static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, 
   std::memset(&a, 0, sizeof(a));
   a.B = d->B; a.T = d->T; a.F_T = d->F_T; a.has_df = df != nullptr;
   a.C = C; a.c = c; a.F = F; a.new_x = new_x; a.new_u = new_u; a.dx = dx; a.du = du; a.dl_dx = dl_dx;
-  a.dx_init = dx_init; a.dC = dC; a.dc = dc; a.dF = dF; a.df = df;
+  a.dx_init = dx_init; a.dC = dC; a.dc = dc; a.dF = dF; a.df = df; a.workspace = workspace;
   rc = (sizeof(R) == 4 ? e->grad32 : e->grad64)(a, (cudaStream_t)stream);
-  if (rc == 0) g_launches.fetch_add(1);
+  if (rc == 0) g_launches.fetch_add(workspace != nullptr ? 2 : 1);
   return rc;
 }
 }  // namespace mpcb200
@@ -178,14 +178,14 @@ int mpcb200_lqr_step_f64(const mpcb200_dims* dims, const mpcb200_params* params,
 int mpcb200_lqr_grad_f32(const mpcb200_dims* dims, const float* C, const float* c, const float* F,
                          const float* new_x, const float* new_u, const float* dx, const float* du,
                          const float* dl_dx, float* dx_init, float* dC, float* dc, float* dF, float* df,
-                         void* stream) {
-  return grad_impl<float>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, stream);
+                         void* workspace, void* stream) {
+  return grad_impl<float>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, workspace, stream);
 }
 int mpcb200_lqr_grad_f64(const mpcb200_dims* dims, const double* C, const double* c, const double* F,
                          const double* new_x, const double* new_u, const double* dx, const double* du,
                          const double* dl_dx, double* dx_init, double* dC, double* dc, double* dF,
-                         double* df, void* stream) {
-  return grad_impl<double>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, stream);
+                         double* df, void* workspace, void* stream) {
+  return grad_impl<double>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, workspace, stream);
 }
 
 int mpcb200_supported(int32_t n_state, int32_t n_ctrl) { return find(n_state, n_ctrl) != nullptr; }

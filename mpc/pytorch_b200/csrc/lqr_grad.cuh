@@ -19,6 +19,7 @@ struct GradArgs {
   int B, T, F_T, has_df;
   const void *C, *c, *F, *new_x, *new_u, *dx, *du, *dl_dx;
   void *dx_init, *dC, *dc, *dF, *df;
+  void* workspace;   // optional: 2*T*B*n elements (lambda, dlambda) -> two-kernel path
 };
 
 template <typename R, int N, int M>
@@ -145,11 +146,176 @@ lqr_grad_kernel(const GradArgs a) {
   if (wr && is_x) ((R*)a.dx_init)[(size_t)b * N + j] = -dlam;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Two-kernel path (used when the caller provides a workspace of 2*T*B*n elements):
+//   1. lqr_costate_kernel: the sequential part - lambda_t, dlambda_t backward in t (reference
+//      :355-385), next step's operands prefetched into registers; writes the costates to the
+//      workspace plus dx_init and df.
+//   2. lqr_outer_kernel: dC, dc, dF for every (t, b) independently (reference :346-353,387-395) -
+//      T x more parallelism than the fused loop, a pure streaming-store kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename R, int N, int M>
+__global__ void __launch_bounds__(GradCfg<R, N, M>::THREADS)
+lqr_costate_kernel(const GradArgs a) {
+  using K = GradCfg<R, N, M>;
+  constexpr int P = K::P, LP = K::LP, PPW = K::PPW;
+  const int T = a.T, B = a.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool writer_lane = lane < PPW * LP;
+  const int pi = writer_lane ? lane / LP : PPW - 1;
+  const int base = pi * LP;
+  const int j = writer_lane ? lane - base : LP - 1;
+  const int b = (blockIdx.x * K::NW + warp) * PPW + pi;
+  const bool valid = b < B;
+  const bool wr = writer_lane && valid;
+  const int bb = valid ? b : 0;
+  const bool is_x = j < N;
+  const int jr = is_x ? j : N - 1;
+  const R* gC = (const R*)a.C;
+  const R* gc = (const R*)a.c;
+  const R* gF = (const R*)a.F;
+  const R* gx = (const R*)a.new_x;
+  const R* gu = (const R*)a.new_u;
+  const R* gdx = (const R*)a.dx;
+  const R* gdu = (const R*)a.du;
+  const R* grx = (const R*)a.dl_dx;
+  R* wl = (R*)a.workspace;
+  R* wd = wl + (size_t)T * B * N;
+  R* of = (R*)a.df;
+
+  struct Tile {
+    R crow[P], fcol[N], tj, dj, cx, rx;
+  };
+  auto fetch = [&](int t, Tile& o) {
+    const size_t tb = (size_t)t * B + bb;
+    o.tj = is_x ? __ldg(gx + tb * N + j) : __ldg(gu + tb * M + (j - N));
+    o.dj = is_x ? __ldg(gdx + tb * N + j) : __ldg(gdu + tb * M + (j - N));
+    const R* Crow = gC + (tb * P + jr) * P;
+#pragma unroll
+    for (int i = 0; i < P; ++i) o.crow[i] = __ldg(Crow + i);
+    o.cx = __ldg(gc + tb * P + jr);
+    o.rx = __ldg(grx + tb * N + jr);
+    if (t < T - 1) {
+      const R* Fc = gF + tb * N * P + jr;
+#pragma unroll
+      for (int k = 0; k < N; ++k) o.fcol[k] = __ldg(Fc + k * P);
+    }
+  };
+  Tile cur, nxt;
+  fetch(T - 1, cur);
+  R lam = R(0), dlam = R(0);
+  for (int t = T - 1; t >= 0; --t) {
+    if (t > 0) fetch(t - 1, nxt);
+    R nl = cur.cx, ndl = -cur.rx;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      nl += cur.crow[i] * shfl(cur.tj, base + i);
+      ndl += cur.crow[i] * shfl(cur.dj, base + i);
+    }
+    if (t < T - 1) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        nl += cur.fcol[k] * shfl(lam, base + k);
+        ndl += cur.fcol[k] * shfl(dlam, base + k);
+      }
+      if (a.has_df && wr && is_x) of[((size_t)t * B + b) * N + j] = -dlam;   // df_t = -dlambda_{t+1}
+    }
+    lam = nl;
+    dlam = ndl;
+    if (wr && is_x) {
+      wl[((size_t)t * B + b) * N + j] = lam;
+      wd[((size_t)t * B + b) * N + j] = dlam;
+    }
+    if (t > 0) cur = nxt;
+  }
+  if (wr && is_x) ((R*)a.dx_init)[(size_t)b * N + j] = -dlam;
+}
+
+template <typename R, int N, int M>
+__global__ void __launch_bounds__(GradCfg<R, N, M>::THREADS)
+lqr_outer_kernel(const GradArgs a) {
+  using K = GradCfg<R, N, M>;
+  constexpr int P = K::P, LP = K::LP, PPW = K::PPW;
+  const int T = a.T, B = a.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (B + PPW - 1) / PPW;                // warp work items per time step
+  const long long item = (long long)blockIdx.x * K::NW + warp;
+  if (item >= (long long)groups * T) return;
+  const int t = (int)(item / groups);
+  const int bw0 = (int)(item - (long long)t * groups) * PPW;
+  const bool writer_lane = lane < PPW * LP;
+  const int pi = writer_lane ? lane / LP : PPW - 1;
+  const int j = writer_lane ? lane - pi * LP : LP - 1;
+  const int b = bw0 + pi;
+  const bool valid = b < B;
+  const int bb = valid ? b : 0;
+  const bool is_x = j < N;
+  const int jr = is_x ? j : N - 1;
+  const int nprob = min(PPW, B - bw0);
+  const size_t tb = (size_t)t * B + bb;
+  const R tj = is_x ? __ldg((const R*)a.new_x + tb * N + j) : __ldg((const R*)a.new_u + tb * M + (j - N));
+  const R dj = is_x ? __ldg((const R*)a.dx + tb * N + j) : __ldg((const R*)a.du + tb * M + (j - N));
+  R* oC = (R*)a.dC;
+  R* oF = (R*)a.dF;
+  if (writer_lane && valid) ((R*)a.dc)[tb * P + j] = -dj;
+  {
+    const size_t off = ((size_t)t * B + bw0) * P * P;
+    constexpr int TOT = PPW * P * P;
+    constexpr int ROUNDS = (TOT + 31) / 32;
+#pragma unroll 4
+    for (int rr = 0; rr < ROUNDS; ++rr) {
+      const int e = rr * 32 + lane;
+      const int ec = e < TOT ? e : TOT - 1;
+      const int pe = ec / (P * P), r = ec - pe * (P * P);
+      const int i = r / P, cc = r - i * P;
+      const R ti = shfl(tj, pe * LP + i);
+      const R di = shfl(dj, pe * LP + i);
+      const R tc = shfl(tj, pe * LP + cc);
+      const R dcc = shfl(dj, pe * LP + cc);
+      if (e < TOT && pe < nprob) oC[off + e] = R(-0.5) * (di * tc + ti * dcc);
+    }
+  }
+  if (t < T - 1) {
+    const R* wl = (const R*)a.workspace;
+    const R* wd = wl + (size_t)T * B * N;
+    const size_t t1 = (size_t)(t + 1) * B + bb;
+    const R lam = __ldg(wl + t1 * N + jr), dlam = __ldg(wd + t1 * N + jr);
+    const size_t off = ((size_t)t * B + bw0) * N * P;
+    constexpr int TOT = PPW * N * P;
+    constexpr int ROUNDS = (TOT + 31) / 32;
+#pragma unroll 4
+    for (int rr = 0; rr < ROUNDS; ++rr) {
+      const int e = rr * 32 + lane;
+      const int ec = e < TOT ? e : TOT - 1;
+      const int pe = ec / (N * P), r = ec - pe * (N * P);
+      const int k = r / P, cc = r - k * P;
+      const R dl = shfl(dlam, pe * LP + k);
+      const R l = shfl(lam, pe * LP + k);
+      const R tc = shfl(tj, pe * LP + cc);
+      const R dc_ = shfl(dj, pe * LP + cc);
+      if (e < TOT && pe < nprob) oF[off + e] = -(dl * tc + l * dc_);
+    }
+  } else if (a.F_T == T) {
+    const size_t off = ((size_t)t * B + bw0) * N * P;
+    for (int e = lane; e < PPW * N * P; e += 32)
+      if (e / (N * P) < nprob) oF[off + e] = R(0);
+  }
+}
+
 template <typename R, int N, int M>
 int launch_grad(const GradArgs& a, cudaStream_t stream) {
   using K = GradCfg<R, N, M>;
   const int grid = (a.B + K::W - 1) / K::W;
-  lqr_grad_kernel<R, N, M><<<grid, K::THREADS, 0, stream>>>(a);
+  if (a.workspace == nullptr) {
+    lqr_grad_kernel<R, N, M><<<grid, K::THREADS, 0, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 5;
+  }
+  lqr_costate_kernel<R, N, M><<<grid, K::THREADS, 0, stream>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return 5;
+  const long long items = (long long)((a.B + K::PPW - 1) / K::PPW) * a.T;
+  const int grid2 = (int)((items + K::NW - 1) / K::NW);
+  lqr_outer_kernel<R, N, M><<<grid2, K::THREADS, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 5;
 }
 

