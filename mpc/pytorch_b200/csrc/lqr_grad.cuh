@@ -30,6 +30,7 @@ struct GradCfg {
   static constexpr int NW = 4;
   static constexpr int W = NW * PPW;
   static constexpr int THREADS = NW * 32;
+  static constexpr int TCHUNK = 4;        // time steps per warp in the outer-product kernel
 };
 
 template <typename R, int N, int M>
@@ -202,11 +203,8 @@ lqr_costate_kernel(const GradArgs a) {
       for (int k = 0; k < N; ++k) o.fcol[k] = __ldg(Fc + k * P);
     }
   };
-  Tile cur, nxt;
-  fetch(T - 1, cur);
   R lam = R(0), dlam = R(0);
-  for (int t = T - 1; t >= 0; --t) {
-    if (t > 0) fetch(t - 1, nxt);
+  auto compute = [&](int t, const Tile& cur) {
     R nl = cur.cx, ndl = -cur.rx;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -227,7 +225,20 @@ lqr_costate_kernel(const GradArgs a) {
       wl[((size_t)t * B + b) * N + j] = lam;
       wd[((size_t)t * B + b) * N + j] = dlam;
     }
-    if (t > 0) cur = nxt;
+  };
+  // register ring of three tiles: operands of steps t-1 and t-2 are in flight while step t computes
+  Tile r0, r1, r2;
+  fetch(T - 1, r0);
+  if (T > 1) fetch(T - 2, r1);
+  for (int t = T - 1; t >= 0; t -= 3) {
+    if (t - 2 >= 0) fetch(t - 2, r2);
+    compute(t, r0);
+    if (t - 1 < 0) break;
+    if (t - 3 >= 0) fetch(t - 3, r0);
+    compute(t - 1, r1);
+    if (t - 2 < 0) break;
+    if (t - 4 >= 0) fetch(t - 4, r1);
+    compute(t - 2, r2);
   }
   if (wr && is_x) ((R*)a.dx_init)[(size_t)b * N + j] = -dlam;
 }
@@ -237,13 +248,15 @@ __global__ void __launch_bounds__(GradCfg<R, N, M>::THREADS)
 lqr_outer_kernel(const GradArgs a) {
   using K = GradCfg<R, N, M>;
   constexpr int P = K::P, LP = K::LP, PPW = K::PPW;
+  constexpr int TC = K::TCHUNK;                           // time steps handled by one warp
   const int T = a.T, B = a.B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int groups = (B + PPW - 1) / PPW;                // warp work items per time step
+  const int groups = (B + PPW - 1) / PPW;                // problem groups (one warp-load each)
+  const int tchunks = (T + TC - 1) / TC;
   const long long item = (long long)blockIdx.x * K::NW + warp;
-  if (item >= (long long)groups * T) return;
-  const int t = (int)(item / groups);
-  const int bw0 = (int)(item - (long long)t * groups) * PPW;
+  if (item >= (long long)groups * tchunks) return;
+  const int tch = (int)(item / groups);
+  const int bw0 = (int)(item - (long long)tch * groups) * PPW;
   const bool writer_lane = lane < PPW * LP;
   const int pi = writer_lane ? lane / LP : PPW - 1;
   const int j = writer_lane ? lane - pi * LP : LP - 1;
@@ -253,53 +266,67 @@ lqr_outer_kernel(const GradArgs a) {
   const bool is_x = j < N;
   const int jr = is_x ? j : N - 1;
   const int nprob = min(PPW, B - bw0);
-  const size_t tb = (size_t)t * B + bb;
-  const R tj = is_x ? __ldg((const R*)a.new_x + tb * N + j) : __ldg((const R*)a.new_u + tb * M + (j - N));
-  const R dj = is_x ? __ldg((const R*)a.dx + tb * N + j) : __ldg((const R*)a.du + tb * M + (j - N));
   R* oC = (R*)a.dC;
   R* oF = (R*)a.dF;
-  if (writer_lane && valid) ((R*)a.dc)[tb * P + j] = -dj;
-  {
-    const size_t off = ((size_t)t * B + bw0) * P * P;
-    constexpr int TOT = PPW * P * P;
-    constexpr int ROUNDS = (TOT + 31) / 32;
-#pragma unroll 4
-    for (int rr = 0; rr < ROUNDS; ++rr) {
-      const int e = rr * 32 + lane;
-      const int ec = e < TOT ? e : TOT - 1;
-      const int pe = ec / (P * P), r = ec - pe * (P * P);
-      const int i = r / P, cc = r - i * P;
-      const R ti = shfl(tj, pe * LP + i);
-      const R di = shfl(dj, pe * LP + i);
-      const R tc = shfl(tj, pe * LP + cc);
-      const R dcc = shfl(dj, pe * LP + cc);
-      if (e < TOT && pe < nprob) oC[off + e] = R(-0.5) * (di * tc + ti * dcc);
-    }
+  const R* wl = (const R*)a.workspace;
+  const R* wd = wl + (size_t)T * B * N;
+
+  // flat-index decode (loop invariant): source lanes of the two factors of every stored element
+  constexpr int TOTC = PPW * P * P, RC = (TOTC + 31) / 32;
+  constexpr int TOTF = PPW * N * P, RF = (TOTF + 31) / 32;
+  int cI[RC], cJ[RC], fK[RF], fJ[RF];
+  unsigned okC = 0u, okF = 0u;
+#pragma unroll
+  for (int rr = 0; rr < RC; ++rr) {
+    const int e = rr * 32 + lane, ec = e < TOTC ? e : TOTC - 1;
+    const int pe = ec / (P * P), r = ec - pe * (P * P);
+    cI[rr] = pe * LP + r / P;
+    cJ[rr] = pe * LP + r % P;
+    if (e < TOTC && pe < nprob) okC |= 1u << rr;
   }
-  if (t < T - 1) {
-    const R* wl = (const R*)a.workspace;
-    const R* wd = wl + (size_t)T * B * N;
-    const size_t t1 = (size_t)(t + 1) * B + bb;
-    const R lam = __ldg(wl + t1 * N + jr), dlam = __ldg(wd + t1 * N + jr);
-    const size_t off = ((size_t)t * B + bw0) * N * P;
-    constexpr int TOT = PPW * N * P;
-    constexpr int ROUNDS = (TOT + 31) / 32;
-#pragma unroll 4
-    for (int rr = 0; rr < ROUNDS; ++rr) {
-      const int e = rr * 32 + lane;
-      const int ec = e < TOT ? e : TOT - 1;
-      const int pe = ec / (N * P), r = ec - pe * (N * P);
-      const int k = r / P, cc = r - k * P;
-      const R dl = shfl(dlam, pe * LP + k);
-      const R l = shfl(lam, pe * LP + k);
-      const R tc = shfl(tj, pe * LP + cc);
-      const R dc_ = shfl(dj, pe * LP + cc);
-      if (e < TOT && pe < nprob) oF[off + e] = -(dl * tc + l * dc_);
+#pragma unroll
+  for (int rr = 0; rr < RF; ++rr) {
+    const int e = rr * 32 + lane, ec = e < TOTF ? e : TOTF - 1;
+    const int pe = ec / (N * P), r = ec - pe * (N * P);
+    fK[rr] = pe * LP + r / P;
+    fJ[rr] = pe * LP + r % P;
+    if (e < TOTF && pe < nprob) okF |= 1u << rr;
+  }
+  static_assert(RC <= 32 && RF <= 32, "decode masks are 32 bit");
+
+  const int t_end = min(T, (tch + 1) * TC);
+  for (int t = tch * TC; t < t_end; ++t) {
+    const size_t tb = (size_t)t * B + bb;
+    const R tj = is_x ? __ldg((const R*)a.new_x + tb * N + j) : __ldg((const R*)a.new_u + tb * M + (j - N));
+    const R dj = is_x ? __ldg((const R*)a.dx + tb * N + j) : __ldg((const R*)a.du + tb * M + (j - N));
+    R lam = R(0), dlam = R(0);
+    if (t < T - 1) {
+      const size_t t1 = (size_t)(t + 1) * B + bb;
+      lam = __ldg(wl + t1 * N + jr);
+      dlam = __ldg(wd + t1 * N + jr);
     }
-  } else if (a.F_T == T) {
-    const size_t off = ((size_t)t * B + bw0) * N * P;
-    for (int e = lane; e < PPW * N * P; e += 32)
-      if (e / (N * P) < nprob) oF[off + e] = R(0);
+    if (writer_lane && valid) ((R*)a.dc)[tb * P + j] = -dj;
+    R* pC = oC + ((size_t)t * B + bw0) * P * P + lane;
+#pragma unroll
+    for (int rr = 0; rr < RC; ++rr) {
+      const R ti = shfl(tj, cI[rr]), di = shfl(dj, cI[rr]);
+      const R tc = shfl(tj, cJ[rr]), dcc = shfl(dj, cJ[rr]);
+      if ((okC >> rr) & 1u) pC[rr * 32] = R(-0.5) * (di * tc + ti * dcc);
+    }
+    if (t < T - 1) {
+      R* pF = oF + ((size_t)t * B + bw0) * N * P + lane;
+#pragma unroll
+      for (int rr = 0; rr < RF; ++rr) {
+        const R dl = shfl(dlam, fK[rr]), l = shfl(lam, fK[rr]);
+        const R tc = shfl(tj, fJ[rr]), dc_ = shfl(dj, fJ[rr]);
+        if ((okF >> rr) & 1u) pF[rr * 32] = -(dl * tc + l * dc_);
+      }
+    } else if (a.F_T == T) {
+      R* pF = oF + ((size_t)t * B + bw0) * N * P + lane;
+#pragma unroll
+      for (int rr = 0; rr < RF; ++rr)
+        if ((okF >> rr) & 1u) pF[rr * 32] = R(0);
+    }
   }
 }
 
@@ -313,7 +340,7 @@ int launch_grad(const GradArgs& a, cudaStream_t stream) {
   }
   lqr_costate_kernel<R, N, M><<<grid, K::THREADS, 0, stream>>>(a);
   if (cudaGetLastError() != cudaSuccess) return 5;
-  const long long items = (long long)((a.B + K::PPW - 1) / K::PPW) * a.T;
+  const long long items = (long long)((a.B + K::PPW - 1) / K::PPW) * ((a.T + K::TCHUNK - 1) / K::TCHUNK);
   const int grid2 = (int)((items + K::NW - 1) / K::NW);
   lqr_outer_kernel<R, N, M><<<grid2, K::THREADS, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 5;

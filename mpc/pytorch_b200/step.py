@@ -22,20 +22,34 @@ def _is_empty(t):
 
 
 def _dense(t, dtype=None):
+    """Dense, detached, right-dtype view of `t` (no copy and no new tensor object when it already is)."""
     if t is None:
         return None
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
-    return t.detach().contiguous()
+    if t.requires_grad:
+        t = t.detach()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 # ----------------------------------------------------------------------------------------------
 # padding to a compiled (n,m) instance (compatibility path for shapes without an exact kernel)
 # ----------------------------------------------------------------------------------------------
 _pairs_cache = None
+_pick_cache = {}
+_smem_fits_cache = {}
 
 
 def _pick_instance(n, m):
+    hit = _pick_cache.get((n, m))
+    if hit is not None:
+        return hit
+    hit = _pick_instance_uncached(n, m)
+    _pick_cache[(n, m)] = hit
+    return hit
+
+
+def _pick_instance_uncached(n, m):
     global _pairs_cache
     if _pairs_cache is None:
         _pairs_cache = _lib.supported_pairs()
@@ -57,8 +71,9 @@ class _Pad:
 
     def __init__(self, n, m, N, M, device):
         self.n, self.m, self.N, self.M = n, m, N, M
-        self.idx = torch.cat((torch.arange(n, device=device), N + torch.arange(m, device=device)))
         self.active = (N, M) != (n, m)
+        self.idx = (torch.cat((torch.arange(n, device=device), N + torch.arange(m, device=device)))
+                    if self.active else None)
 
     def mat_pp(self, C):          # [..., p, p] -> [..., P, P]
         out = C.new_zeros(*C.shape[:-2], self.N + self.M, self.N + self.M)
@@ -87,6 +102,21 @@ class _Pad:
         out = u.new_full((*u.shape[:-1], self.M), fill)
         out[..., : self.m] = u
         return out
+
+
+class _on_device:
+    """`torch.cuda.device(dev)` only when `dev` is not already current (the guard costs microseconds)."""
+
+    def __init__(self, dev):
+        self.guard = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -167,8 +197,12 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     need_gains = want_gains or not do_rollout
     if not need_gains:
         # long horizons do not fit shared memory: the kernel then keeps gains in a caller buffer
-        smem = L.mpcb200_step_smem_bytes(ctypes.byref(dims), C_.element_size())
-        need_gains = smem > 227 * 1024
+        key = (N, M, T, C_.element_size())
+        fits = _smem_fits_cache.get(key)
+        if fits is None:
+            fits = L.mpcb200_step_smem_bytes(ctypes.byref(dims), C_.element_size()) <= 227 * 1024
+            _smem_fits_cache[key] = fits
+        need_gains = not fits
     if need_gains:
         Ks = torch.empty(T, B, M, N, dtype=dtype, device=dev)
         ks = torch.empty(T, B, M, dtype=dtype, device=dev)
@@ -176,7 +210,7 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
                     delta_u=float(delta_u) if delta_u is not None else 0.0,
                     ls_decay=float(linesearch_decay))
     fn = L.mpcb200_lqr_step_f32 if dtype == torch.float32 else L.mpcb200_lqr_step_f64
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr(C_), ptr(c_), ptr(F_), ptr(f_), ptr(x0_),
                 ptr(cx_), ptr(cu_), ptr(lo_t), ptr(hi_t), ptr(zmask), ptr(new_x), ptr(new_u),
                 ptr(costs), ptr(fdn), ptr(alphas), ptr(du_first), ptr(qp_iters), ptr(free_mask), ptr(status),
@@ -224,7 +258,7 @@ def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_
     L = _lib.lib()
     fn = L.mpcb200_lqr_grad_f32 if dtype == torch.float32 else L.mpcb200_lqr_grad_f64
     ws = torch.empty(2 * T * B * N, dtype=dtype, device=dev)     # costates: enables the two-kernel path
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = fn(ctypes.byref(dims), ptr(C_), ptr(c_), ptr(F_), ptr(nx_), ptr(nu_), ptr(dx_), ptr(du_),
                 ptr(r_), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), ptr(ws), stream_handle(dev))
     check(rc, "mpcb200_lqr_grad")
