@@ -91,8 +91,17 @@ struct StepCfg {
   static constexpr int OFF_END = OFF_hi + W * M;
   static constexpr int STAGE_BYTES = round_up(OFF_END * (int)sizeof(R) + round_up(W * M, 16), 128);
   // per-problem scratch (elements)
-  static constexpr int SC_V = 0;                 // N x VS  value matrix
-  static constexpr int SC_v = SC_V + N * VS;     // VS      value vector
+  static constexpr int PS = round_up(P, 4);      // padded row stride of the W exchange buffer
+  // VREG: the value matrix stays in registers and the rows of F are register resident during the
+  // two products (needs N*P registers per lane; small problems only).  Measured on B200, config 3:
+  // 25 % fewer shared-memory loads but one more exchange per step -> 38.9 us vs 38.0 us (B=4096) and
+  // 250 us vs 230 us (B=32768).  Off by default; kept as a knob.
+#ifndef MPCB_VREG
+#define MPCB_VREG 0
+#endif
+  static constexpr bool VREG = MPCB_VREG && CPL == 1 && N * P * (int)sizeof(R) <= 400;
+  static constexpr int SC_V = 0;                 // VREG: N x PS  W = V F exchange; else N x VS value matrix
+  static constexpr int SC_v = SC_V + N * (VREG ? PS : VS);     // VS      value vector
   static constexpr int SC_K = SC_v + VS;         // M x VS (+ M) K_t,k_t exchange when gains are not smem resident
   static constexpr int KT = M * VS + round_up(M, 4);  // elements per (problem, t) of the gain store
   static constexpr int SC_Q = SC_K + KT;         // M x VS  Q_xu exchange (row a = Q[:n, n+a])
@@ -364,6 +373,8 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   R kprev[M];
 #pragma unroll
   for (int q = 0; q < M; ++q) kprev[q] = R(0);
+  Vec<R, N> Vreg;                         // VREG: column j of the value matrix
+  Vreg.zero();
 
   // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
   for (int t = T - 1; t >= 0; --t) {
@@ -413,25 +424,50 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
     if (t < T - 1) {                            // Q = C + F'VF, q = c_back + F'v  (:66-70)
       Vec<R, N> Fcol[CPL], Wc[CPL];
 #pragma unroll
-      for (int sl = 0; sl < CPL; ++sl) {
-        Fcol[sl].gather(st + oF + cc[sl], P);
-        Wc[sl].zero();
+      for (int sl = 0; sl < CPL; ++sl) Fcol[sl].gather(st + oF + cc[sl], P);
+      if constexpr (K::VREG) {
+        // V stays in registers: lane i holds V[:, i] (used as row i - V is symmetric up to round-off and
+        // the transposed use is stable).  Rows of F are loaded ONCE into
+        // registers and feed both products: W[i, :] = sum_k V[i,k] F[k, :] on the state lanes, then,
+        // after a transpose of W through shared memory, Q[:, j] += sum_k F[k, :]' W[k, j] on every lane.
+        Vec<R, P> Frow[N];
+        static_for<0, N>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          constexpr int AK = k % 2 == 0 ? A_2P : align_elems<R>(P);
+          Frow[k].template load<(AK < A_NP ? AK : A_NP)>(st + oF + k * P);
+        });
+        Vec<R, P> Wrow;
+        Wrow.zero();
+#pragma unroll
+        for (int k = 0; k < N; ++k) Wrow.axpy(Frow[k], Vreg.get(k));
+        if (wsl[0] && isx[0]) {
+          R* dst = Vs + cc[0] * K::PS;
+#pragma unroll
+          for (int i = 0; i < P; ++i) dst[i] = Wrow.get(i);
+        }
+        __syncwarp();
+        Wc[0].gather(Vs + cc[0], K::PS);          // column j of W
+#pragma unroll
+        for (int k = 0; k < N; ++k) Qc[0].axpy(Frow[k], Wc[0].get(k));
+      } else {
+#pragma unroll
+        for (int sl = 0; sl < CPL; ++sl) Wc[sl].zero();
+#pragma unroll
+        for (int k = 0; k < N; ++k) {             // W[:, c] = V F[:, c]; each V column load feeds CPL columns
+          Vec<R, N> Vcol;                         // Vs holds V transposed: row k of Vs == column k of V
+          Vcol.template load<EA>(Vs + k * VS);
+#pragma unroll
+          for (int sl = 0; sl < CPL; ++sl) Wc[sl].axpy(Vcol, Fcol[sl].get(k));
+        }
+        static_for<0, N>([&](auto kc) {           // Q[:, c] += F' W[:, c]; rows of F are contiguous
+          constexpr int k = decltype(kc)::value;
+          constexpr int AK = k % 2 == 0 ? A_2P : align_elems<R>(P);
+          Vec<R, P> Frow;
+          Frow.template load<(AK < A_NP ? AK : A_NP)>(st + oF + k * P);
+#pragma unroll
+          for (int sl = 0; sl < CPL; ++sl) Qc[sl].axpy(Frow, Wc[sl].get(k));
+        });
       }
-#pragma unroll
-      for (int k = 0; k < N; ++k) {             // W[:, c] = V F[:, c]; each V column load feeds CPL columns
-        Vec<R, N> Vcol;                         // Vs holds V transposed: row k of Vs == column k of V
-        Vcol.template load<EA>(Vs + k * VS);
-#pragma unroll
-        for (int sl = 0; sl < CPL; ++sl) Wc[sl].axpy(Vcol, Fcol[sl].get(k));
-      }
-      static_for<0, N>([&](auto kc) {           // Q[:, c] += F' W[:, c]; rows of F are contiguous
-        constexpr int k = decltype(kc)::value;
-        constexpr int AK = k % 2 == 0 ? A_2P : align_elems<R>(P);
-        Vec<R, P> Frow;
-        Frow.template load<(AK < A_NP ? AK : A_NP)>(st + oF + k * P);
-#pragma unroll
-        for (int sl = 0; sl < CPL; ++sl) Qc[sl].axpy(Frow, Wc[sl].get(k));
-      });
       Vec<R, N> vv;
       vv.template load<EA>(vs);
 #pragma unroll
@@ -598,11 +634,18 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
     for (int sl = 0; sl < CPL; ++sl) {
       if (wsl[sl] && isx[sl]) {
-        R* dst = Vs + cc[sl] * VS;        // column c of V, stored as row c
+        if constexpr (!K::VREG) {
+          R* dst = Vs + cc[sl] * VS;      // column c of V, stored as row c
 #pragma unroll
-        for (int i = 0; i < N; ++i) dst[i] = Vn[sl].get(i);
+          for (int i = 0; i < N; ++i) dst[i] = Vn[sl].get(i);
+        }
         vs[cc[sl]] = vn[sl];
       }
+    }
+    if constexpr (K::VREG) {              // V[:, j] stays in this lane's registers (control lanes: zero)
+#pragma unroll
+      for (int k2 = 0; k2 < Vec<R, N>::NP; ++k2)
+        Vreg.p[k2] = isx[0] ? Vn[0].p[k2] : P2<R>{R(0), R(0)};
     }
     TICK(tk, 6)
     __syncwarp();
