@@ -62,8 +62,12 @@ MPCB_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uin
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// CTA-wide named barrier.  `bar.sync` is the .aligned form (the whole warp must execute it
+// convergently); callers reach it right after lane-divergent code, so reconverge first and use the
+// non-aligned `barrier.sync` (compute-sanitizer synccheck flagged the aligned form here).
 MPCB_DEV void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+  __syncwarp();
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------ compile-time helpers
