@@ -50,6 +50,7 @@ struct StepArgs {
 template <typename R, int N, int M>
 struct StepCfg {
   static constexpr int P = N + M;
+  static constexpr int EA = 16 / (int)sizeof(R);
   static_assert(P <= 32, "one problem must fit a warp");
   // columns per lane: 2 when the problem is wide enough (halves the shared-memory operand traffic
   // per problem and doubles the independent FMA streams per lane), else 1.  Slot 0 of every lane
@@ -78,11 +79,40 @@ struct StepCfg {
   static constexpr int THREADS = (NW + 1) * 32;
   static constexpr int S = MPCB_STAGES;   // ring stages
   static constexpr int VS = round_up(N, 4);
-  static constexpr int EA = 16 / (int)sizeof(R);
-  // stage tile offsets (elements); every sub-tile starts 16-byte aligned because W % 4 == 0
+  // Per-problem strides of the C and F tiles inside a stage.  The PPW problems of a warp read the same
+  // tile offsets at the same time, so their bank windows must not overlap: pad the stride (in 16-byte
+  // steps) to the value with the fewest overlapping banks; each problem's tile is then its own bulk copy.
+  static constexpr int bank_overlap(int stride) {
+    int words = (int)sizeof(R) / 4, hit = 0;
+    for (int a = 0; a < PPW; ++a)
+      for (int b2 = a + 1; b2 < PPW; ++b2) {
+        int d = ((b2 - a) * stride * words) % 32;
+        if (d > 16) d = 32 - d;
+        int ov = P * words - d;
+        hit += ov > 0 ? ov : 0;
+      }
+    return hit;
+  }
+  static constexpr int pick_stride(int dense) {
+    if ((dense * (int)sizeof(R)) % 16 != 0 || PPW == 1) return dense;   // per-problem bulk copies need 16B multiples
+    int best = dense, best_hit = bank_overlap(dense);
+    for (int pad = EA; pad <= 32; pad += EA) {
+      int h = bank_overlap(dense + pad);
+      if (h < best_hit) { best = dense + pad; best_hit = h; }
+    }
+    return best;
+  }
+  // Measured on B200, config 3: the PPW small bulk copies per tensor cost more than the removed bank
+  // conflicts save (51 us vs 38 us).  Off by default; kept as a knob.
+#ifndef MPCB_PADTILES
+#define MPCB_PADTILES 0
+#endif
+  static constexpr int CS = MPCB_PADTILES ? pick_stride(P * P) : P * P;
+  static constexpr int FS = MPCB_PADTILES ? pick_stride(N * P) : N * P;
+  // stage tile offsets (elements); every sub-tile starts 16-byte aligned (span_ok / padded strides)
   static constexpr int OFF_C = 0;
-  static constexpr int OFF_F = OFF_C + W * P * P;
-  static constexpr int OFF_c = OFF_F + W * N * P;
+  static constexpr int OFF_F = OFF_C + W * CS;
+  static constexpr int OFF_c = OFF_F + W * FS;
   static constexpr int OFF_f = OFF_c + W * P;
   static constexpr int OFF_x = OFF_f + W * N;
   static constexpr int OFF_u = OFF_x + W * N;
@@ -258,8 +288,20 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
         if (needf) bytes += (uint32_t)cnt * N * SZ;
         if (a.bounds_kind == 2) bytes += 2u * cnt * M * SZ;
         mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(st + K::OFF_C, gC + tb * P * P, (uint32_t)cnt * P * P * SZ, &full[s]);
-        if (needF) bulk_g2s(st + K::OFF_F, gF + tb * N * P, (uint32_t)cnt * N * P * SZ, &full[s]);
+        if constexpr (K::CS == P * P) {
+          bulk_g2s(st + K::OFF_C, gC + tb * P * P, (uint32_t)cnt * P * P * SZ, &full[s]);
+        } else {
+          for (int q = 0; q < cnt; ++q)
+            bulk_g2s(st + K::OFF_C + q * K::CS, gC + (tb + q) * P * P, (uint32_t)P * P * SZ, &full[s]);
+        }
+        if (needF) {
+          if constexpr (K::FS == N * P) {
+            bulk_g2s(st + K::OFF_F, gF + tb * N * P, (uint32_t)cnt * N * P * SZ, &full[s]);
+          } else {
+            for (int q = 0; q < cnt; ++q)
+              bulk_g2s(st + K::OFF_F + q * K::FS, gF + (tb + q) * N * P, (uint32_t)N * P * SZ, &full[s]);
+          }
+        }
         bulk_g2s(st + K::OFF_c, gc + tb * P, (uint32_t)cnt * P * SZ, &full[s]);
         if (needf) bulk_g2s(st + K::OFF_f, gf + tb * N, (uint32_t)cnt * N * SZ, &full[s]);
         bulk_g2s(st + K::OFF_x, gx + tb * N, (uint32_t)cnt * N * SZ, &full[s]);
@@ -273,8 +315,9 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
       auto cp = [&](R* dst, const R* src, int nelem) {
         for (int i = lane; i < nelem; i += 32) dst[i] = __ldg(src + i);
       };
-      cp(st + K::OFF_C, gC + tb * P * P, cnt * P * P);
-      if (needF) cp(st + K::OFF_F, gF + tb * N * P, cnt * N * P);
+      for (int q = 0; q < cnt; ++q) cp(st + K::OFF_C + q * K::CS, gC + (tb + q) * P * P, P * P);
+      if (needF)
+        for (int q = 0; q < cnt; ++q) cp(st + K::OFF_F + q * K::FS, gF + (tb + q) * N * P, N * P);
       cp(st + K::OFF_c, gc + tb * P, cnt * P);
       if (needf) cp(st + K::OFF_f, gf + tb * N, cnt * N);
       cp(st + K::OFF_x, gx + tb * N, cnt * N);
@@ -316,7 +359,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   constexpr bool BOX = MODE == MODE_BOX;
   constexpr int A_N = align_elems<R>(N), A_M = align_elems<R>(M);
   constexpr int A_ROW = (P % 2 == 0) ? 2 : 1;   // row r*P of a per-problem tile (pair aligned for even P)
-  constexpr int A_2P = align_elems<R>(2 * P), A_NP = align_elems<R>(N * P);
+  constexpr int A_2P = align_elems<R>(2 * P), A_NP = align_elems<R>(K::FS);
   const int T = a.T, B = a.B;
   const bool writer_lane = lane < PPW * LP;
   const int pi = writer_lane ? lane / LP : PPW - 1;
@@ -341,7 +384,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   }
 
   // per-problem element offsets inside a stage (loop invariant)
-  const int oC = K::OFF_C + pw * P * P, oF = K::OFF_F + pw * N * P;
+  const int oC = K::OFF_C + pw * K::CS, oF = K::OFF_F + pw * K::FS;
   const int oc = K::OFF_c + pw * P, of_ = K::OFF_f + pw * N, ox = K::OFF_x + pw * N, ou = K::OFF_u + pw * M;
   const int olo = K::OFF_lo + pw * M, ohi = K::OFF_hi + pw * M;
 
@@ -861,7 +904,7 @@ lqr_step_kernel(const StepArgs a) {
     for (int s = 0; s < K::S; ++s)
       for (int i = tid; i < K::W * K::P; i += K::THREADS) {
         R* Ct = reinterpret_cast<R*>(stage_base + (size_t)s * K::STAGE_BYTES) + K::OFF_C;
-        Ct[(i / K::P) * K::P * K::P + (i % K::P) * (K::P + 1)] = R(1);   // C = I
+        Ct[(i / K::P) * K::CS + (i % K::P) * (K::P + 1)] = R(1);   // C = I
       }
   }
   __syncthreads();
