@@ -136,6 +136,17 @@ int mpcb200_lqr_grad_f64(const mpcb200_dims* dims,
                          double* dx_init, double* dC, double* dc, double* dF, double* df,
                          void* workspace, void* stream);
 
+/*
+ * Nominal trajectory under LinDx dynamics: replaces util.get_traj for LinDx (reference
+ * mpc/util.py:102-126, called once per iLQR iteration at mpc/mpc.py:251):
+ *   x[0] = x_init;  x[t+1] = F[t] [x[t]; u[t]] + f[t]   (f may be NULL; dims->has_f)
+ * x[T,B,n] is written; only dims->{B,T,n,m,F_T,has_f} are read.
+ */
+int mpcb200_rollout_f32(const mpcb200_dims* dims, const float* F, const float* f, const float* x_init,
+                        const float* u, float* x, void* stream);
+int mpcb200_rollout_f64(const mpcb200_dims* dims, const double* F, const double* f, const double* x_init,
+                        const double* u, double* x, void* stream);
+
 /* 1 if a kernel instance for (n_state, n_ctrl) is compiled in, else 0. */
 int mpcb200_supported(int32_t n_state, int32_t n_ctrl);
 

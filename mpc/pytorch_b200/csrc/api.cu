@@ -5,6 +5,7 @@
 
 #include "../../../include/mpcb200.h"
 #include "lqr_grad.cuh"
+#include "lqr_rollout.cuh"
 #include "lqr_step.cuh"
 
 namespace mpcb200 {
@@ -13,6 +14,8 @@ namespace mpcb200 {
   int step_f64__##n##_##m(const StepArgs&, int, cudaStream_t);              \
   int grad_f32__##n##_##m(const GradArgs&, cudaStream_t);                   \
   int grad_f64__##n##_##m(const GradArgs&, cudaStream_t);                   \
+  int roll_f32__##n##_##m(const RolloutArgs&, cudaStream_t);                \
+  int roll_f64__##n##_##m(const RolloutArgs&, cudaStream_t);                \
   size_t smem_f32__##n##_##m(int);                                          \
   size_t smem_f64__##n##_##m(int);
 #include "instances.def"
@@ -26,11 +29,13 @@ struct Entry {
   int (*grad64)(const GradArgs&, cudaStream_t);
   size_t (*smem32)(int);
   size_t (*smem64)(int);
+  int (*roll32)(const RolloutArgs&, cudaStream_t);
+  int (*roll64)(const RolloutArgs&, cudaStream_t);
 };
 static const Entry kTable[] = {
 #define MPCB200_INST(n, m)                                                                  \
   {n, m, step_f32__##n##_##m, step_f64__##n##_##m, grad_f32__##n##_##m, grad_f64__##n##_##m, \
-   smem_f32__##n##_##m, smem_f64__##n##_##m},
+   smem_f32__##n##_##m, smem_f64__##n##_##m, roll_f32__##n##_##m, roll_f64__##n##_##m},
 #include "instances.def"
 #undef MPCB200_INST
 };
@@ -149,6 +154,25 @@ static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, 
   if (rc == 0) g_launches.fetch_add(workspace != nullptr ? 2 : 1);
   return rc;
 }
+template <typename R>
+static int rollout_impl(const mpcb200_dims* d, const R* F, const R* f, const R* x_init, const R* u, R* x,
+                        void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if (x_init == nullptr || u == nullptr || x == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (d->T > 1 && F == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (d->has_f && f == nullptr) return MPCB200_ERR_NULL_POINTER;
+  const Entry* e = find(d->n, d->m);
+  if (e == nullptr) return MPCB200_ERR_UNSUPPORTED_DIMS;
+  if (max_smem_optin() <= 0) return MPCB200_ERR_NO_DEVICE;
+  RolloutArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = d->B; a.T = d->T; a.has_f = d->has_f ? 1 : 0;
+  a.F = F; a.f = f; a.x_init = x_init; a.u = u; a.x = x;
+  rc = (sizeof(R) == 4 ? e->roll32 : e->roll64)(a, (cudaStream_t)stream);
+  if (rc == 0) g_launches.fetch_add(1);
+  return rc;
+}
 }  // namespace mpcb200
 
 using namespace mpcb200;
@@ -186,6 +210,15 @@ int mpcb200_lqr_grad_f64(const mpcb200_dims* dims, const double* C, const double
                          const double* dl_dx, double* dx_init, double* dC, double* dc, double* dF,
                          double* df, void* workspace, void* stream) {
   return grad_impl<double>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, workspace, stream);
+}
+
+int mpcb200_rollout_f32(const mpcb200_dims* dims, const float* F, const float* f, const float* x_init,
+                        const float* u, float* x, void* stream) {
+  return rollout_impl<float>(dims, F, f, x_init, u, x, stream);
+}
+int mpcb200_rollout_f64(const mpcb200_dims* dims, const double* F, const double* f, const double* x_init,
+                        const double* u, double* x, void* stream) {
+  return rollout_impl<double>(dims, F, f, x_init, u, x, stream);
 }
 
 int mpcb200_supported(int32_t n_state, int32_t n_ctrl) { return find(n_state, n_ctrl) != nullptr; }

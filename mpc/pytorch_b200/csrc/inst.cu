@@ -1,6 +1,7 @@
 // inst.cu - compiled once per (INST_N, INST_M) pair (see Makefile): explicit launchers for
 // the step and gradient kernels in float and double.
 #include "lqr_grad.cuh"
+#include "lqr_rollout.cuh"
 #include "lqr_step.cuh"
 
 #ifndef INST_N
@@ -23,6 +24,12 @@ int MPCB_CAT(grad_f32_, , INST_N, INST_M)(const GradArgs& a, cudaStream_t s) {
 }
 int MPCB_CAT(grad_f64_, , INST_N, INST_M)(const GradArgs& a, cudaStream_t s) {
   return launch_grad<double, INST_N, INST_M>(a, s);
+}
+int MPCB_CAT(roll_f32_, , INST_N, INST_M)(const RolloutArgs& a, cudaStream_t s) {
+  return launch_rollout<float, INST_N, INST_M>(a, s);
+}
+int MPCB_CAT(roll_f64_, , INST_N, INST_M)(const RolloutArgs& a, cudaStream_t s) {
+  return launch_rollout<double, INST_N, INST_M>(a, s);
 }
 size_t MPCB_CAT(smem_f32_, , INST_N, INST_M)(int T) { return step_smem_query<float, INST_N, INST_M>(T); }
 size_t MPCB_CAT(smem_f64_, , INST_N, INST_M)(int T) { return step_smem_query<double, INST_N, INST_M>(T); }

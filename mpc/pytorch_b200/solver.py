@@ -49,6 +49,9 @@ def get_traj(T, u, x_init, dynamics):
             F, f = _detach(dynamics.F), _detach(dynamics.f)
             if f is not None and f.nelement() > 0:
                 assert f.shape == F.shape[:3]
+            if x_init.is_cuda and x_init.dtype in (torch.float32, torch.float64) and F.dtype == x_init.dtype:
+                from .step import rollout_raw                 # one kernel instead of T-1 bmm/cat/add launches
+                return rollout_raw(x_init.shape[1], u.shape[2], T, _detach(x_init), _detach(u), F, f)
             for t in range(T - 1):
                 nx = _mv(F[t], torch.cat((xs[t], u[t]), 1))
                 if f is not None and f.nelement() > 0:

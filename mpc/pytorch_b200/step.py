@@ -272,6 +272,33 @@ def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_
     return dx_init, dC, dc, dF, df
 
 
+def rollout_raw(n_state, n_ctrl, T, x_init, u, F, f=None):
+    """x = get_traj(T, u, x_init, LinDx(F, f)) in ONE kernel (reference mpc/util.py:102-126)."""
+    dtype, dev = x_init.dtype, x_init.device
+    if not x_init.is_cuda:
+        raise MpcB200Error("mpc.pytorch_b200 runs on CUDA tensors only (no CPU fallback)")
+    n, m = n_state, n_ctrl
+    B = x_init.shape[0]
+    N, M = _pick_instance(n, m)
+    pad = _Pad(n, m, N, M, dev)
+    x0_, u_ = _dense(x_init, dtype), _dense(u, dtype)
+    F_ = _dense(F, dtype) if not _is_empty(F) else None
+    f_ = _dense(f, dtype) if not _is_empty(f) else None
+    if pad.active:
+        x0_, u_ = pad.vec_n(x0_), pad.vec_m(u_)
+        F_ = pad.mat_np(F_) if F_ is not None else None
+        f_ = pad.vec_n(f_) if f_ is not None else None
+    x = torch.empty(T, B, N, dtype=dtype, device=dev)
+    dims = Dims(B=B, T=T, n=N, m=M, F_T=F_.shape[0] if F_ is not None else T - 1, has_f=int(f_ is not None),
+                bounds_kind=0, has_zero_mask=0, has_delta_u=0, max_ls_iter=1, pnqp_max_iter=1, do_rollout=1)
+    L = _lib.lib()
+    fn = L.mpcb200_rollout_f32 if dtype == torch.float32 else L.mpcb200_rollout_f64
+    with _on_device(dev):
+        rc = fn(ctypes.byref(dims), ptr(F_), ptr(f_), ptr(x0_), ptr(u_), ptr(x), stream_handle(dev))
+    check(rc, "mpcb200_rollout")
+    return x[..., :n] if pad.active else x
+
+
 # ----------------------------------------------------------------------------------------------
 # split-mode rollout for nn.Module dynamics / costs (cannot run inside the kernel)
 # ----------------------------------------------------------------------------------------------

@@ -131,3 +131,24 @@ def test_analytic_and_finite_diff_linearisation_agree():
         outs.append(mpc.MPC(5, 1, T, grad_method=gm).linearize_dynamics(x, u, dx, diff=False))
     for F2, f2 in outs[1:]:
         assert maxdiff(F2, outs[0][0]) < 1e-4 and maxdiff(f2, outs[0][1]) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(9, 7, 8, 2, torch.float32, True), (5, 6, 3, 4, torch.float64, False),
+                                   (4, 5, 6, 1, torch.float64, True), (3, 1, 4, 2, torch.float32, True)])
+def test_rollout_kernel_matches_reference_get_traj(shape):
+    """mpcb200_rollout (get_traj for LinDx, reference mpc/util.py:102-126) vs the torch recurrence."""
+    from mpc.pytorch_b200.step import rollout_raw
+    B, T, n, m, dtype, with_f = shape
+    C, c, F, f, x0 = [v.to(DEV) if v is not None else None for v in gen_problem(70, B, T, n, m, dtype, True, with_f)]
+    u = torch.randn(T, B, m, dtype=dtype, device=DEV)
+    if T == 1:
+        F = torch.zeros(0, B, n, n + m, dtype=dtype, device=DEV)
+        f = None
+    got = rollout_raw(n, m, T, x0, u, F, f)
+    xs = [x0]
+    for k in range(T - 1):
+        nx = torch.einsum("bij,bj->bi", F[k], torch.cat((xs[k], u[k]), 1))
+        xs.append(nx + f[k] if f is not None else nx)
+    want = torch.stack(xs)
+    assert got.shape == want.shape
+    assert maxdiff(got, want) <= (1e-12 if dtype == torch.float64 else 2e-5) * max(1.0, float(want.abs().max()))
