@@ -147,6 +147,21 @@ int mpcb200_rollout_f32(const mpcb200_dims* dims, const float* F, const float* f
 int mpcb200_rollout_f64(const mpcb200_dims* dims, const double* F, const double* f, const double* x_init,
                         const double* u, double* x, void* stream);
 
+/*
+ * Standalone projected-Newton box QP, n <= 8: replaces pnqp(H,q,lower,upper,x_init,n_iter) of the
+ * reference (mpc/pnqp.py:5-82) for batches of small QPs  min 0.5 x'Hx + q'x, lower <= x <= upper.
+ * H[B,n,n] q,lower,upper[B,n]; x_init[B,n] or NULL (cold start -H^{-1}q).  Outputs x[B,n],
+ * H_free[B,n,n] (the masked matrix H_ of the returning iteration, whose LU the reference returns),
+ * If[B,n] uint8 free set, iters[B] (the reference's `i`), status[B] optional (MPCB200_ST_* bits).
+ * Per-problem control flow (what the reference computes for n_batch = 1).
+ */
+int mpcb200_pnqp_f32(int32_t B, int32_t n, const float* H, const float* q, const float* lower,
+                     const float* upper, const float* x_init, int32_t n_iter, float* x, float* H_free,
+                     uint8_t* If, int32_t* iters, int32_t* status, void* stream);
+int mpcb200_pnqp_f64(int32_t B, int32_t n, const double* H, const double* q, const double* lower,
+                     const double* upper, const double* x_init, int32_t n_iter, double* x, double* H_free,
+                     uint8_t* If, int32_t* iters, int32_t* status, void* stream);
+
 /* 1 if a kernel instance for (n_state, n_ctrl) is compiled in, else 0. */
 int mpcb200_supported(int32_t n_state, int32_t n_ctrl);
 

@@ -32,7 +32,7 @@ _lib = None
 # every symbol include/mpcb200.h declares
 EXPORTED_SYMBOLS = (
     "mpcb200_lqr_step_f32", "mpcb200_lqr_step_f64", "mpcb200_lqr_grad_f32", "mpcb200_lqr_grad_f64",
-    "mpcb200_rollout_f32", "mpcb200_rollout_f64",
+    "mpcb200_rollout_f32", "mpcb200_rollout_f64", "mpcb200_pnqp_f32", "mpcb200_pnqp_f64",
     "mpcb200_supported", "mpcb200_supported_list", "mpcb200_launch_count",
     "mpcb200_step_smem_bytes", "mpcb200_version", "mpcb200_strerror",
 )
@@ -62,6 +62,10 @@ def lib():
     for name in ("mpcb200_rollout_f32", "mpcb200_rollout_f64"):
         fn = getattr(L, name)
         fn.argtypes = [ctypes.POINTER(Dims)] + [vp] * 6
+        fn.restype = ctypes.c_int
+    for name in ("mpcb200_pnqp_f32", "mpcb200_pnqp_f64"):
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.c_int32, ctypes.c_int32] + [vp] * 5 + [ctypes.c_int32] + [vp] * 6
         fn.restype = ctypes.c_int
     L.mpcb200_supported.argtypes = [ctypes.c_int32, ctypes.c_int32]
     L.mpcb200_supported.restype = ctypes.c_int

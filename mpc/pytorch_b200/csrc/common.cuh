@@ -47,6 +47,19 @@ MPCB_DEV bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (mbarrier.test_wait): lets a consumer look at the NEXT stage while it still has
+// work of the current one in flight, so the wait latency is off the per-step critical path
+MPCB_DEV bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 MPCB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
   // plain try_wait blocks in hardware for a bounded time; the suspend-hint form compiles to a
   // NANOSLEEP polling loop (measured) whose wake-up granularity hurts a latency-bound consumer

@@ -82,6 +82,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 def test_drop_in_import_paths():
     from mpc import mpc as m
     from mpc.lqr_step import LQRStep  # noqa: F401
+    from mpc.pnqp import pnqp  # noqa: F401
     import inspect
     sig = inspect.signature(m.MPC.__init__)
     assert list(sig.parameters)[1:] == [

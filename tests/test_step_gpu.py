@@ -259,3 +259,21 @@ def test_config3_full_size_properties():
         assert maxdiff(nx[:, idx][:, okp], ob.new_x[:, okp]) < tol
         if bounds is not None:
             assert torch.equal(o["free_mask"][:, idx].cpu().bool()[:, okp], ob.free_masks[:, okp])
+
+
+@pytest.mark.parametrize("name", ["pnqp_f64_cold", "pnqp_f64_warm", "pnqp_f32_cold", "pnqp_f64_n1"])
+def test_standalone_pnqp_matches_reference_fixture(name):
+    """mpc.pnqp.pnqp on the GPU vs the reference's stored outputs and the per-problem oracle."""
+    from mpc.pnqp import pnqp
+    g = load_golden(name)
+    H, q, lo, hi = (g[k].to(DEV) for k in ("H", "q", "lower", "upper"))
+    x0 = g["x_init"].to(DEV) if "x_init" in g else None
+    x, Hf, If, it = pnqp(H, q, lo, hi, x_init=x0, n_iter=20)
+    xo, Ho, Ifo, ito = orc.pnqp(g["H"], g["q"], g["lower"], g["upper"], x_init=g.get("x_init"), n_iter=20,
+                                coupled=False)
+    f64 = g["H"].dtype == torch.float64
+    assert maxdiff(x, xo) <= (1e-10 if f64 else 2e-6)
+    assert torch.equal(If.cpu().bool(), Ifo.bool()) and it == int(ito.max())
+    assert maxdiff(Hf, Ho) <= (1e-12 if f64 else 1e-6)
+    assert maxdiff(x, g["x"]) <= 2e-4                      # reference (batch-coupled) result
+    assert torch.equal(If.cpu().bool(), g["If"].bool())    # active set: bit exact
