@@ -47,8 +47,8 @@ MPCB_DEV bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
       : "memory");
   return ok != 0;
 }
-// non-blocking probe (mbarrier.test_wait): lets a consumer look at the NEXT stage while it still has
-// work of the current one in flight, so the wait latency is off the per-step critical path
+// non-blocking probe (mbarrier.test_wait).  Probing the NEXT stage at the end of a step (to take the
+// try_wait latency off the per-step path) was measured: 38.8 us vs 38.1 us at config 3 - not used.
 MPCB_DEV bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

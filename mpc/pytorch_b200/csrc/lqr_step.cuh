@@ -404,7 +404,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 
   int stg = 0;
   uint32_t ph = 0;
-  bool ready = false;                      // result of the early probe of full[stg]
   unsigned status = 0u;
   R oldcost_part = R(0);
 #ifdef MPCB_TIMING
@@ -425,13 +424,12 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #ifdef MPCB_TIMING
     c0 = clock64();
 #endif
-    if (!ready) mbar_wait(&full[stg], ph);
+    mbar_wait(&full[stg], ph);
     TICK(tk, 0)
     if (a.debug & 2) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stg]);
       if (++stg == K::S) { stg = 0; ph ^= 1u; }
-      ready = false;
       continue;
     }
     const R* st = (const R*)(stage_base + (size_t)stg * K::STAGE_BYTES);
@@ -696,7 +694,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stg]);
     if (++stg == K::S) { stg = 0; ph ^= 1u; }
-    ready = mbar_test(&full[stg], ph);      // probe the next tile now; its latency overlaps the loop tail
     TICK(tk, 7)
   }
 
@@ -734,14 +731,13 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #ifdef MPCB_TIMING
       c0 = clock64();
 #endif
-      if (!ready) mbar_wait(&full[stg], ph);
+      mbar_wait(&full[stg], ph);
       TICK(tf, 0)
       if (a.debug & 2) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stg]);
         if (++stg == K::S) { stg = 0; ph ^= 1u; }
-        ready = false;
-        continue;
+          continue;
       }
       const R* st = (const R*)(stage_base + (size_t)stg * K::STAGE_BYTES);
       const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
@@ -843,7 +839,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stg]);
       if (++stg == K::S) { stg = 0; ph ^= 1u; }
-      ready = mbar_test(&full[stg], ph);
       TICK(tf, 4)
     }
     if (writer_lane) red[j] = cpart;
