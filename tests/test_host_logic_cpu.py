@@ -1,0 +1,58 @@
+"""CPU: host-side logic that needs no kernel - byte accounting of bench.py and the zero-padding that
+embeds an (n,m) problem into a compiled (N,M) kernel instance (checked with the oracle)."""
+import pytest
+import torch
+
+from oracle import lqr_oracle as orc
+from tests.helpers import gen_problem, maxdiff, nominal_controls
+
+
+def test_bytes_per_solve_matches_survey_table():
+    """820 / 8788 / 17128 / 17448 / 157928 bytes per solve for configs 1-5."""
+    import bench
+    assert bench.bytes_per_solve(5, 3, 1) == 820
+    assert bench.bytes_per_solve(25, 5, 1) == 8788
+    assert bench.bytes_per_solve(20, 8, 2) == 17128
+    assert bench.bytes_per_solve(20, 8, 2, tensor_bounds=True) == 17448
+    assert bench.bytes_per_solve(50, 16, 4) == 157928
+
+
+@pytest.mark.parametrize("shape,bounds", [((3, 3), 0.3), ((6, 1), None), ((5, 3), "tensor")])
+def test_padding_embedding_is_exact(shape, bounds):
+    """step._Pad: the padded problem solved by the ORACLE equals the original problem (so a padded
+    kernel launch computes the same thing); padded controls stay at 0 and free."""
+    from mpc.pytorch_b200.step import _Pad
+    n, m = shape
+    N, M = n + 2, m + 1
+    B, T = 4, 6
+    C, c, F, f, x0 = gen_problem(90, B, T, n, m, torch.float64, time_varying=True)
+    u, ul, uu = nominal_controls(90, B, T, m, torch.float64, bounds)
+    x = orc.get_traj(T, u, x0, F, f)
+    ref = orc.lqr_step_forward(n, m, T, x0, C, c, F, f, x, u, u_lower=ul, u_upper=uu, coupled=False)
+    pad = _Pad(n, m, N, M, torch.device("cpu"))
+    if bounds is None:
+        lo = hi = None
+    else:
+        lo = pad.vec_m(ul if torch.is_tensor(ul) else torch.full((T, B, m), ul, dtype=torch.float64), -1.0)
+        hi = pad.vec_m(uu if torch.is_tensor(uu) else torch.full((T, B, m), uu, dtype=torch.float64), 1.0)
+    got = orc.lqr_step_forward(N, M, T, pad.vec_n(x0), pad.mat_pp(C), pad.vec_p(c), pad.mat_np(F), pad.vec_n(f),
+                               pad.vec_n(x), pad.vec_m(u), u_lower=lo, u_upper=hi, coupled=False)
+    assert maxdiff(got.new_x[..., :n], ref.new_x) < 1e-10 and maxdiff(got.new_u[..., :m], ref.new_u) < 1e-10
+    assert float(got.new_x[..., n:].abs().max()) == 0.0 and float(got.new_u[..., m:].abs().max()) == 0.0
+    assert maxdiff(got.costs, ref.costs) < 1e-10
+    assert maxdiff(got.Ks[..., :m, :n], ref.Ks) < 1e-10
+    if bounds is not None:
+        assert torch.equal(got.free_masks[..., :m], ref.free_masks) and bool(got.free_masks[..., m:].all())
+
+
+def test_reference_full_du_norm_quirk():
+    """The reference views a [T,m,B] buffer as [B,T*m] (mpc/lqr_step.py:244-245): identical to the
+    per-problem norm only for B == 1; the sum of squares is preserved."""
+    from mpc.pytorch_b200.step import reference_full_du_norm
+    du = torch.randn(5, 3, 2, dtype=torch.float64)
+    q = reference_full_du_norm(du)
+    true = du.pow(2).sum((0, 2)).sqrt()
+    assert abs(float(q.pow(2).sum() - true.pow(2).sum())) < 1e-12
+    assert not torch.allclose(q, true)
+    one = torch.randn(5, 1, 2, dtype=torch.float64)
+    assert torch.allclose(reference_full_du_norm(one), one.pow(2).sum((0, 2)).sqrt())
