@@ -911,6 +911,7 @@ lqr_step_kernel(const StepArgs a) {
   if (warp == K::NW) {
     step_producer<R, N, M>(a, stage_base, full, empty, votes, b0, cnt, lane);
   } else {
+
     step_consumer<R, N, M, MODE>(a, stage_base, full, empty, votes, scratch, kstore, b0, warp, lane);
   }
 }
