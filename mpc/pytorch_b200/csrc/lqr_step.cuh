@@ -7,7 +7,9 @@
 // Mapping (designed for B200, not translated from the reference's per-op loop):
 //  * P = n+m lanes own one problem; lane j owns COLUMN j of every p-wide matrix of that
 //    problem (Q_t, F_t, C_t) and, for j < n, column j of the value matrix V and of K_t.
-//    32/P problems share a warp, 4 consumer warps + 1 producer warp form a CTA.
+//    32/P problems share a warp; NW consumer warps (the smallest count whose spans stay 16-byte
+//    aligned: small CTAs = fine load-balance granularity, the batch is < 1 wave) + 1 producer warp
+//    form a CTA.  The dense products use packed FFMA2 (two fp32 FMAs per lane per instruction).
 //  * the producer warp streams the per-time-step tiles C[t],F[t],c[t],f[t],x_bar[t],u_bar[t]
 //    (+ tensor bounds) of the CTA's W consecutive problems - contiguous in the reference's
 //    time-major layout - into a 3-stage shared-memory ring with 1-D bulk TMA
@@ -21,6 +23,10 @@
 //    (unless T is too long for shared memory, then a caller-provided Ks/ks buffer is used).
 //  * line search: per-problem alpha; a CTA repeats the rollout while any of its problems is
 //    worse and iterations remain - per problem this is exactly the reference's batch loop.
+//  * MODE (template): PLAIN / BOX (pnqp) / MASK (u_zero_I adjoint solve) - no mode branches at run time.
+// Compile-time knobs kept from measured experiments (all off / default): MPCB_STAGES, MPCB_CPL,
+// MPCB_VREG, MPCB_PADTILES, MPCB_TIMING (per-phase clock64 report); env MPCB200_DEBUG (1: no data
+// movement, 2: no math) for bottleneck isolation.  See DESIGN.md section 7.
 #pragma once
 #include <cstdio>
 #include "common.cuh"
