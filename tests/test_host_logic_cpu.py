@@ -56,3 +56,59 @@ def test_reference_full_du_norm_quirk():
     assert not torch.allclose(q, true)
     one = torch.randn(5, 1, 2, dtype=torch.float64)
     assert torch.allclose(reference_full_du_norm(one), one.pow(2).sum((0, 2)).sqrt())
+
+
+def test_linearize_dynamics_methods_agree_on_cpu():
+    """linearize_dynamics is pure torch (no kernel): ANALYTIC / AUTO_DIFF / FINITE_DIFF agree to 1e-4 and
+    reproduce the dynamics to first order (reference tests/test_mpc.py:747-799)."""
+    from mpc.pytorch_b200.solver import MPC, GradMethods
+    from tests.cartpole import Cartpole, initial_states
+
+    class CartpoleAnalytic(Cartpole):
+        def grad_input(self, x, u):
+            xg, ug = x.detach().requires_grad_(True), u.detach().requires_grad_(True)
+            with torch.enable_grad():
+                y = self.forward(xg, ug)
+                rows = [torch.autograd.grad(y[:, j].sum(), [xg, ug], retain_graph=True) for j in range(5)]
+            return torch.stack([r[0] for r in rows], 1), torch.stack([r[1] for r in rows], 1)
+
+    T, B = 5, 3
+    dx = CartpoleAnalytic()
+    x0 = initial_states(B, 2, torch.float64)
+    u = 0.5 * torch.randn(T, B, 1, dtype=torch.float64)
+    xs = [x0]
+    for t in range(T - 1):
+        xs.append(dx(xs[t], u[t]))
+    x = torch.stack(xs)
+    outs = [MPC(5, 1, T, grad_method=gm).linearize_dynamics(x, u, dx, diff=False)
+            for gm in (GradMethods.ANALYTIC, GradMethods.AUTO_DIFF, GradMethods.FINITE_DIFF)]
+    for F2, f2 in outs[1:]:
+        assert maxdiff(F2, outs[0][0]) < 1e-4 and maxdiff(f2, outs[0][1]) < 1e-4
+    F, f = outs[0]
+    pred = torch.einsum("tbij,tbj->tbi", F, torch.cat((x[:-1], u[:-1]), 2)) + f
+    assert maxdiff(pred, x[1:]) < 1e-10                      # exact at the expansion point
+    Fd, fd = MPC(5, 1, T, grad_method=GradMethods.AUTO_DIFF).linearize_dynamics(x, u, dx, diff=True)
+    assert maxdiff(Fd, F) < 1e-12
+
+
+def test_approximate_cost_recovers_a_quadratic():
+    """approximate_cost (reference mpc/mpc.py:447-487) on a known quadratic returns its C and c."""
+    from mpc.pytorch_b200.solver import MPC
+    T, B, n, m = 4, 3, 3, 2
+    p = n + m
+    g = torch.Generator().manual_seed(0)
+    L = torch.randn(p, p, generator=g, dtype=torch.float64)
+    Cq = L @ L.T + torch.eye(p, dtype=torch.float64)
+    cq = torch.randn(p, generator=g, dtype=torch.float64)
+
+    class Quad(torch.nn.Module):
+        def forward(self, tau):
+            return 0.5 * (tau @ Cq * tau).sum(-1) + tau @ cq
+
+    x = torch.randn(T, B, n, generator=g, dtype=torch.float64)
+    u = torch.randn(T, B, m, generator=g, dtype=torch.float64)
+    H, lin, costs = MPC(n, m, T).approximate_cost(x, u, Quad(), diff=False)
+    assert maxdiff(H, Cq.expand(T, B, p, p)) < 1e-10
+    assert maxdiff(lin, cq.expand(T, B, p)) < 1e-10
+    tau = torch.cat((x, u), 2)
+    assert maxdiff(costs, 0.5 * (tau @ Cq * tau).sum(-1) + tau @ cq) < 1e-10
