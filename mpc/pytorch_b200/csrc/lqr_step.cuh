@@ -244,8 +244,18 @@ MPCB_DEV void pnqp_lane(const R (&H)[M][M], const R (&q)[M], const R (&lo)[M], c
       if (again) alpha *= R(0.1);
       ++count;
     } while (again && count < 10);
+    // A step that does not move x (bitwise) is a fixed point of the whole iteration: g, the active set,
+    // H_, dx and the Armijo trials of every later iteration are identical.  In fp32 this is how the
+    // reference fails to converge (|dx| stays just above 1e-4 while x + alpha dx rounds back to x);
+    // returning now with the outcome of iteration max_iter-1 is exactly what the remaining iterations
+    // would produce, without ~18 x 10 wasted Armijo trials that made this warp the kernel's tail.
+    bool moved = false;
 #pragma unroll
-    for (int a = 0; a < M; ++a) x[a] = mx[a];  // :78
+    for (int a = 0; a < M; ++a) {
+      moved = moved || !(mx[a] == x[a]);
+      x[a] = mx[a];                            // :78
+    }
+    if (!moved) break;
   }
   iters = max_iter - 1;                        // :80-82
   conv = false;
