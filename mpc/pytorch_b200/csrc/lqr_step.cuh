@@ -143,7 +143,19 @@ struct StepCfg {
   static constexpr int SC_Q = SC_K + KT;         // M x VS  Q_xu exchange (row a = Q[:n, n+a])
   static constexpr int SC_X = SC_Q + M * VS;     // 2 x VS  rollout state exchange
   static constexpr int SC_R = SC_X + 2 * VS;     // cost reduction
-  static constexpr int SC_RAW = SC_R + round_up(P, 4);
+  // n=16, m=4, fp32: optional tensor-core path for the two dense products of the sweep (mma.sync m16n8k8
+  // TF32 in three passes, fp32 accumulate; Q comes back through a P x 24 shared buffer).  Parity-green, 3.3x
+  // fewer shared-memory wavefronts - but measured SLOWER inside this kernel (757 vs 677 us at B=4096, T=50):
+  // with the gain store in shared memory only 2 CTAs (8 warps) fit an SM, so the step is latency bound and
+  // the mma chain is no shorter than the FFMA2 one.  The standalone probe (tools/mma_probe.cu, all warps
+  // resident) needs 2.5 us per step for the same products: the win needs an occupancy fix first (gains in
+  // global/L2 or a smaller ring).  Off by default.
+#ifndef MPCB_MMA16
+#define MPCB_MMA16 0
+#endif
+  static constexpr bool MMA16 = MPCB_MMA16 && N == 16 && M == 4 && sizeof(R) == 4 && CPL == 1;
+  static constexpr int SC_QT = SC_R + round_up(P, 4);
+  static constexpr int SC_RAW = SC_QT + (MMA16 ? P * 24 : 0);
   static constexpr int SCR = (SC_RAW % 32 == 0 || SC_RAW % 32 == 16) ? SC_RAW + 4 : SC_RAW;
   static constexpr int HDR_BYTES = 256;          // 2*S mbarriers + 32 vote words
   static size_t smem_bytes(int T, bool k_in_smem) {
@@ -359,6 +371,99 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core helpers (mma.sync.m16n8k8, TF32 operands, fp32 accumulate; 3xTF32 = hi*hi + hi*lo + lo*hi)
+// ---------------------------------------------------------------------------------------------
+MPCB_DEV void tf32_split(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+MPCB_DEV void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+MPCB_DEV void mma_3xtf32(float (&d)[4], const unsigned (&ah)[4], const unsigned (&al)[4],
+                         const unsigned (&bh)[2], const unsigned (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// Q = C + F'(V F) for ONE problem per warp, n=16, p=20 (measured in tools/mma_probe.cu).  F, C: dense
+// row-major tiles in shared memory; Vt[c*VS + i] = V[i][c]; the result is written to QT[a*24 + b].
+MPCB_DEV void wq_products_mma16(const float* Fp, const float* Cp, const float* Vt, int VS, float* QT, int lane) {
+  constexpr int NN = 16, PP = 20;
+  const int g = lane >> 2, t = lane & 3;
+  unsigned Ah[2][2][4], Al[2][2][4];          // A fragments of F': rows a = mt*16+g(+8), cols k = ks*8+t(+4)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int a = mt * 16 + g + (r & 1) * 8, k = ks * 8 + t + (r >> 1) * 4;
+        tf32_split(a < PP ? Fp[k * PP + a] : 0.f, Ah[mt][ks][r], Al[mt][ks][r]);
+      }
+  float Wt[2][2][4];                          // W' = F'V in accumulator layout
+  {
+    unsigned Vh[2][2][2], Vl[2][2][2];        // B fragments of V: k = ks*8+t(+4), n = nt*8+g
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          tf32_split(Vt[(nt * 8 + g) * VS + ks * 8 + t + r * 4], Vh[ks][nt][r], Vl[ks][nt][r]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Wt[mt][nt][r] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) mma_3xtf32(Wt[mt][nt], Ah[mt][ks], Al[mt][ks], Vh[ks][nt], Vl[ks][nt]);
+      }
+  }
+  unsigned Wh[2][3][2], Wl[2][3][2];          // accumulator layout -> B fragments of W (quad shuffles)
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      const int mt = nt >> 1, hi8 = (nt & 1) * 2;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int src = (lane & ~3) | ((t + r * 4) >> 1);
+        const float xe = __shfl_sync(0xffffffffu, Wt[mt][ks][hi8 + 0], src);
+        const float xo = __shfl_sync(0xffffffffu, Wt[mt][ks][hi8 + 1], src);
+        tf32_split((t & 1) ? xo : xe, Wh[ks][nt][r], Wl[ks][nt][r]);
+      }
+    }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      float acc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int a = mt * 16 + g + (r >> 1) * 8, b = nt * 8 + 2 * t + (r & 1);
+        acc[r] = (a < PP && b < PP) ? Cp[a * PP + b] : 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) mma_3xtf32(acc, Ah[mt][ks], Al[mt][ks], Wh[ks][nt], Wl[ks][nt]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int a = mt * 16 + g + h * 8;
+        if (a < PP) *reinterpret_cast<float2*>(QT + a * 24 + nt * 8 + 2 * t) = make_float2(acc[2 * h], acc[2 * h + 1]);
+      }
+    }
+  (void)NN;
+}
+MPCB_DEV void wq_products_mma16(const double*, const double*, const double*, int, double*, int) {}   // never used
+
 // ---------------------------------------------------------------------------------------------
 // consumer warps.  MODE (compile time): 0 plain (no bounds, no mask), 1 box (pnqp; optional
 // u_zero_I), 2 mask (u_zero_I only - the adjoint solve).
@@ -484,7 +589,14 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
       Vec<R, N> Fcol[CPL], Wc[CPL];
 #pragma unroll
       for (int sl = 0; sl < CPL; ++sl) Fcol[sl].gather(st + oF + cc[sl], P);
-      if constexpr (K::VREG) {
+      if constexpr (K::MMA16) {
+        // tensor-core path: operands are fetched once per warp as fragments instead of once per lane
+        R* QT = scr + K::SC_QT;
+        wq_products_mma16(st + oF, st + oC, Vs, VS, QT, lane);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < P; ++i) Qc[0].set(i, QT[i * 24 + cc[0]]);   // column j of Q (C already included)
+      } else if constexpr (K::VREG) {
         // V stays in registers: lane i holds V[:, i] (used as row i - V is symmetric up to round-off and
         // the transposed use is stable).  Rows of F are loaded ONCE into
         // registers and feed both products: W[i, :] = sum_k V[i,k] F[k, :] on the state lanes, then,
