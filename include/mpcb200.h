@@ -174,6 +174,11 @@ uint64_t mpcb200_launch_count(void);
 /* Dynamic shared memory (bytes) the step kernel needs for these dims / element size (4 or 8); 0 if unsupported. */
 size_t mpcb200_step_smem_bytes(const mpcb200_dims* dims, int32_t elem_size);
 
+/* 1 if the step kernel wants caller-provided Ks/ks buffers for these dims: either the gain store of all
+ * T steps does not fit shared memory, or (one-problem-per-warp shapes such as n=16) moving it out of shared
+ * memory is what lets enough warps be resident.  Pass Ks[T,B,m,n], ks[T,B,m] then. */
+int mpcb200_step_prefers_workspace(const mpcb200_dims* dims, int32_t elem_size);
+
 int mpcb200_version(void);
 const char* mpcb200_strerror(int code);
 

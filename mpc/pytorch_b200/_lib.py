@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "mpcb200_lqr_step_f32", "mpcb200_lqr_step_f64", "mpcb200_lqr_grad_f32", "mpcb200_lqr_grad_f64",
     "mpcb200_rollout_f32", "mpcb200_rollout_f64", "mpcb200_pnqp_f32", "mpcb200_pnqp_f64",
     "mpcb200_supported", "mpcb200_supported_list", "mpcb200_launch_count",
-    "mpcb200_step_smem_bytes", "mpcb200_version", "mpcb200_strerror",
+    "mpcb200_step_smem_bytes", "mpcb200_step_prefers_workspace", "mpcb200_version", "mpcb200_strerror",
 )
 
 
@@ -75,6 +75,8 @@ def lib():
     L.mpcb200_launch_count.restype = ctypes.c_uint64
     L.mpcb200_step_smem_bytes.argtypes = [ctypes.POINTER(Dims), ctypes.c_int32]
     L.mpcb200_step_smem_bytes.restype = ctypes.c_size_t
+    L.mpcb200_step_prefers_workspace.argtypes = [ctypes.POINTER(Dims), ctypes.c_int32]
+    L.mpcb200_step_prefers_workspace.restype = ctypes.c_int
     L.mpcb200_version.argtypes = []
     L.mpcb200_version.restype = ctypes.c_int
     L.mpcb200_strerror.argtypes = [ctypes.c_int]

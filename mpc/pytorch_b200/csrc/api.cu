@@ -14,6 +14,8 @@ namespace mpcb200 {
   int step_f64__##n##_##m(const StepArgs&, int, cudaStream_t);              \
   int grad_f32__##n##_##m(const GradArgs&, cudaStream_t);                   \
   int grad_f64__##n##_##m(const GradArgs&, cudaStream_t);                   \
+  int pws_f32__##n##_##m(int, int);                                         \
+  int pws_f64__##n##_##m(int, int);                                         \
   int roll_f32__##n##_##m(const RolloutArgs&, cudaStream_t);                \
   int roll_f64__##n##_##m(const RolloutArgs&, cudaStream_t);                \
   size_t smem_f32__##n##_##m(int);                                          \
@@ -31,11 +33,14 @@ struct Entry {
   size_t (*smem64)(int);
   int (*roll32)(const RolloutArgs&, cudaStream_t);
   int (*roll64)(const RolloutArgs&, cudaStream_t);
+  int (*pws32)(int, int);
+  int (*pws64)(int, int);
 };
 static const Entry kTable[] = {
 #define MPCB200_INST(n, m)                                                                  \
   {n, m, step_f32__##n##_##m, step_f64__##n##_##m, grad_f32__##n##_##m, grad_f64__##n##_##m, \
-   smem_f32__##n##_##m, smem_f64__##n##_##m, roll_f32__##n##_##m, roll_f64__##n##_##m},
+   smem_f32__##n##_##m, smem_f64__##n##_##m, roll_f32__##n##_##m, roll_f64__##n##_##m,   \
+   pws_f32__##n##_##m, pws_f64__##n##_##m},
 #include "instances.def"
 #undef MPCB200_INST
 };
@@ -238,6 +243,15 @@ size_t mpcb200_step_smem_bytes(const mpcb200_dims* dims, int32_t elem_size) {
   const Entry* e = find(dims->n, dims->m);
   if (e == nullptr) return 0;
   return elem_size == 8 ? e->smem64(dims->T) : e->smem32(dims->T);
+}
+
+int mpcb200_step_prefers_workspace(const mpcb200_dims* dims, int32_t elem_size) {
+  if (dims == nullptr) return 0;
+  const Entry* e = find(dims->n, dims->m);
+  if (e == nullptr) return 0;
+  int ms = max_smem_optin();
+  if (ms <= 0) ms = 227 * 1024;       // no device visible (CPU-side query): assume B200's opt-in limit
+  return elem_size == 8 ? e->pws64(dims->T, ms) : e->pws32(dims->T, ms);
 }
 
 int mpcb200_version(void) { return MPCB200_VERSION; }

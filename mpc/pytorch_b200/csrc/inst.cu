@@ -31,6 +31,8 @@ int MPCB_CAT(roll_f32_, , INST_N, INST_M)(const RolloutArgs& a, cudaStream_t s) 
 int MPCB_CAT(roll_f64_, , INST_N, INST_M)(const RolloutArgs& a, cudaStream_t s) {
   return launch_rollout<double, INST_N, INST_M>(a, s);
 }
+int MPCB_CAT(pws_f32_, , INST_N, INST_M)(int T, int ms) { return step_prefers_workspace<float, INST_N, INST_M>(T, ms); }
+int MPCB_CAT(pws_f64_, , INST_N, INST_M)(int T, int ms) { return step_prefers_workspace<double, INST_N, INST_M>(T, ms); }
 size_t MPCB_CAT(smem_f32_, , INST_N, INST_M)(int T) { return step_smem_query<float, INST_N, INST_M>(T); }
 size_t MPCB_CAT(smem_f64_, , INST_N, INST_M)(int T) { return step_smem_query<double, INST_N, INST_M>(T); }
 

@@ -147,7 +147,7 @@ struct StepCfg {
   // TF32 in three passes, fp32 accumulate; Q comes back through a P x 24 shared buffer).  Parity-green, 3.3x
   // fewer shared-memory wavefronts - but measured SLOWER inside this kernel (757 vs 677 us at B=4096, T=50):
   // with the gain store in shared memory only 2 CTAs (8 warps) fit an SM, so the step is latency bound and
-  // the mma chain is no shorter than the FFMA2 one.  The standalone probe (tools/mma_probe.cu, all warps
+  // the mma chain is no shorter than the FFMA2 one (and with the gains in global memory the kernel is register limited).  The standalone probe (tools/mma_probe.cu, all warps
   // resident) needs 2.5 us per step for the same products: the win needs an occupancy fix first (gains in
   // global/L2 or a smaller ring).  Off by default.
 #ifndef MPCB_MMA16
@@ -157,6 +157,16 @@ struct StepCfg {
   static constexpr int SC_QT = SC_R + round_up(P, 4);
   static constexpr int SC_RAW = SC_QT + (MMA16 ? P * 24 : 0);
   static constexpr int SCR = (SC_RAW % 32 == 0 || SC_RAW % 32 == 16) ? SC_RAW + 4 : SC_RAW;
+  // KREDUCE: when the gains live in the caller's Ks/ks buffer (long horizons / large n), lane i reads only
+  // column i of K_t and the products are butterfly-reduced over the n state lanes (needs one problem per
+  // warp and n a power of two).  For such shapes the gain store is moved out of shared memory on purpose
+  // (GAIN_SMEM_LIMIT bytes per problem): it is what limits the resident warps per SM.
+  static constexpr bool KREDUCE = CPL == 1 && PPW == 1 && (N & (N - 1)) == 0;
+  static constexpr int GAIN_SMEM_LIMIT = 6144;
+  static bool prefers_workspace(int T, int max_smem_optin) {
+    return smem_bytes(T, true) > (size_t)max_smem_optin ||
+           (KREDUCE && (size_t)T * KT * sizeof(R) > (size_t)GAIN_SMEM_LIMIT);
+  }
   static constexpr int HDR_BYTES = 256;          // 2*S mbarriers + 32 vote words
   static size_t smem_bytes(int T, bool k_in_smem) {
     size_t b = HDR_BYTES + (size_t)S * STAGE_BYTES + (size_t)W * SCR * sizeof(R);
@@ -854,6 +864,22 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
     for (int sl = 0; sl < CPL; ++sl) xown[sl] = valid ? gx0[(size_t)b * N + fr[sl]] : R(0);
     R cpart = R(0), dun2 = R(0);
+    R kcol[M], kff[M];                           // KREDUCE with gains in global memory: column of K_t, k_t
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+      kcol[q] = R(0);
+      kff[q] = R(0);
+    }
+    if constexpr (K::KREDUCE) {
+      if (!a.k_in_smem) {
+        const size_t kb = (size_t)(valid ? b : 0) * M;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          kcol[q] = __ldcg(gKs + (kb + q) * N + fr[0]);
+          kff[q] = __ldcg(gks + kb + q);
+        }
+      }
+    }
     size_t orow = (size_t)b;                     // t*B + b
     for (int t = 0; t < T; ++t, orow += (size_t)B) {
 #ifdef MPCB_TIMING
@@ -884,6 +910,28 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
           Vec<R, N> Krow;
           Krow.template load<EA>(Kt + q * VS);
           u[q] = (Krow.dot(dxv) + ubar.get(q)) + alpha * Kt[M * VS + q];      // (:192)
+        }
+      } else if constexpr (K::KREDUCE) {
+        // gains in the caller's buffer: this lane holds column cc of K_t and k_t (prefetched one step
+        // ahead); K dx is reduced over the n state lanes with a butterfly, then broadcast
+        const R dxi = xown[0] - st[ox + fr[0]];
+        R part[M];
+#pragma unroll
+        for (int q = 0; q < M; ++q) part[q] = isx[0] ? kcol[q] * dxi : R(0);
+#pragma unroll
+        for (int off = N / 2; off >= 1; off >>= 1) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], off);
+        }
+#pragma unroll
+        for (int q = 0; q < M; ++q) u[q] = (shfl(part[q], base) + ubar.get(q)) + alpha * kff[q];
+        if (t + 1 < T) {                         // prefetch the next step's column (L2 hit) behind this step
+          const size_t kb = ((size_t)(t + 1) * B + (valid ? b : 0)) * M;
+#pragma unroll
+          for (int q = 0; q < M; ++q) {
+            kcol[q] = __ldcg(gKs + (kb + q) * N + fr[0]);
+            kff[q] = __ldcg(gks + kb + q);
+          }
         }
       } else {
         const R* Kg = gKs + ((size_t)t * B + (valid ? b : 0)) * M * N;
@@ -1050,11 +1098,12 @@ int launch_step_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stre
   StepArgs a = args;
   size_t smem = K::smem_bytes(a.T, true);
   a.k_in_smem = 1;
-  if (smem > (size_t)max_smem_optin) {
+  const bool have_ws = a.Ks != nullptr && a.ks != nullptr;
+  if (smem > (size_t)max_smem_optin || (K::prefers_workspace(a.T, max_smem_optin) && have_ws && a.do_rollout)) {
     a.k_in_smem = 0;
     smem = K::smem_bytes(a.T, false);
     if (smem > (size_t)max_smem_optin) return 4;
-    if (a.do_rollout && (a.Ks == nullptr || a.ks == nullptr)) return 4;
+    if (a.do_rollout && !have_ws) return 4;
   }
   auto kern = lqr_step_kernel<R, N, M, MODE>;
   static int configured = 0;
@@ -1074,6 +1123,11 @@ int launch_step(const StepArgs& a, int max_smem_optin, cudaStream_t stream) {
   if (a.bounds_kind != 0) return launch_step_mode<R, N, M, MODE_BOX>(a, max_smem_optin, stream);
   if (a.has_mask) return launch_step_mode<R, N, M, MODE_MASK>(a, max_smem_optin, stream);
   return launch_step_mode<R, N, M, MODE_PLAIN>(a, max_smem_optin, stream);
+}
+
+template <typename R, int N, int M>
+int step_prefers_workspace(int T, int max_smem_optin) {
+  return StepCfg<R, N, M>::prefers_workspace(T, max_smem_optin) ? 1 : 0;
 }
 
 template <typename R, int N, int M>

@@ -200,7 +200,7 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
         key = (N, M, T, C_.element_size())
         fits = _smem_fits_cache.get(key)
         if fits is None:
-            fits = L.mpcb200_step_smem_bytes(ctypes.byref(dims), C_.element_size()) <= 227 * 1024
+            fits = not L.mpcb200_step_prefers_workspace(ctypes.byref(dims), C_.element_size())
             _smem_fits_cache[key] = fits
         need_gains = not fits
     if need_gains:
