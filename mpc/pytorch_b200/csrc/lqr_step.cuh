@@ -1106,12 +1106,14 @@ int launch_step_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stre
     if (a.do_rollout && !have_ws) return 4;
   }
   auto kern = lqr_step_kernel<R, N, M, MODE>;
-  static int configured = 0;
-  if (configured < (int)smem) {
+  static int configured[64] = {0};           // per device: the opt-in shared-memory attribute is per context
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 6;
+  if (configured[dev] < (int)smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) !=
         cudaSuccess)
       return 5;
-    configured = max_smem_optin;
+    configured[dev] = max_smem_optin;
   }
   const int grid = (a.B + K::W - 1) / K::W;
   kern<<<grid, K::THREADS, smem, stream>>>(a);
