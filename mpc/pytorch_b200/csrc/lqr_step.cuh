@@ -25,8 +25,8 @@
 //    worse and iterations remain - per problem this is exactly the reference's batch loop.
 //  * MODE (template): PLAIN / BOX (pnqp) / MASK (u_zero_I adjoint solve) - no mode branches at run time.
 // Compile-time knobs kept from measured experiments (all off / default): MPCB_STAGES, MPCB_CPL,
-// MPCB_VREG, MPCB_PADTILES, MPCB_TIMING (per-phase clock64 report); env MPCB200_DEBUG (1: no data
-// movement, 2: no math) for bottleneck isolation.  See DESIGN.md section 7.
+// MPCB_VREG, MPCB_PADTILES, MPCB_MMA16, MPCB_TIMING (per-phase clock64 report); with -DMPCB_DEBUG_KNOBS the
+// env var MPCB200_DEBUG (1: no data movement, 2: no math) isolates bottlenecks.  See DESIGN.md section 7.
 #pragma once
 #include <cstdio>
 #include "common.cuh"
