@@ -112,3 +112,22 @@ def test_approximate_cost_recovers_a_quadratic():
     assert maxdiff(lin, cq.expand(T, B, p)) < 1e-10
     tau = torch.cat((x, u), 2)
     assert maxdiff(costs, 0.5 * (tau @ Cq * tau).sum(-1) + tau @ cq) < 1e-10
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU arm = oracle port) must print one JSON line with the contract keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=240, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
