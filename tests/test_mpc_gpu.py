@@ -152,3 +152,20 @@ def test_rollout_kernel_matches_reference_get_traj(shape):
     want = torch.stack(xs)
     assert got.shape == want.shape
     assert maxdiff(got, want) <= (1e-12 if dtype == torch.float64 else 2e-5) * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("bound", [None, 0.35])
+def test_mpc_solution_is_the_box_qp_optimum(bound):
+    """reference tests/test_mpc.py:91-194: the iLQR fixed point computed on the GPU equals the optimum of the
+    box-constrained problem found by an independent solver (scipy L-BFGS-B on the condensed problem)."""
+    from mpc import mpc
+    from tests.test_oracle_golden import _condensed_box_lqr_scipy
+    B, T, n, m = 2, 5, 3, 2
+    C, c, F, f, x0 = gen_problem(41, B, T, n, m, torch.float64, time_varying=True)
+    lo, hi = (-1e4, 1e4) if bound is None else (-bound, bound)
+    kw = {} if bound is None else dict(u_lower=lo, u_upper=hi)
+    x, u, _ = mpc.MPC(n, m, T, lqr_iter=30, eps=1e-10, verbose=-1, exit_unconverged=False, **kw)(
+        x0.to(DEV), mpc.QuadCost(C.to(DEV), c.to(DEV)), mpc.LinDx(F.to(DEV), f.to(DEV)))
+    for b in range(B):
+        xs, us = _condensed_box_lqr_scipy(C[:, b], c[:, b], F[:, b], f[:, b], x0[b], lo, hi)
+        assert maxdiff(u[:, b], us) < 2e-4 and maxdiff(x[:, b], xs) < 2e-4
