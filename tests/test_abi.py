@@ -83,6 +83,9 @@ def test_drop_in_import_paths():
     from mpc import mpc as m
     from mpc.lqr_step import LQRStep  # noqa: F401
     from mpc.pnqp import pnqp  # noqa: F401
+    from mpc import util
+    assert all(hasattr(util, k) for k in ("bger", "bmv", "bquad", "bdot", "bdiag", "eclamp", "get_traj", "get_cost",
+                                           "table_log", "detach_maybe", "data_maybe", "jacobian", "expandParam"))
     import inspect
     sig = inspect.signature(m.MPC.__init__)
     assert list(sig.parameters)[1:] == [
