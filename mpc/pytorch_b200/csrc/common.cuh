@@ -212,6 +212,27 @@ struct Vec {
 #pragma unroll
     for (int k = 0; k < NP; ++k) p[k] = {tmp[2 * k], tmp[2 * k + 1]};
   }
+  // store L contiguous elements; V = vector width (elements) the address is aligned to
+  template <int V>
+  MPCB_DEV void store(R* ptr) const {
+    constexpr int LV = (L / V) * V;
+    if constexpr (V == 4 && sizeof(R) == 4) {
+#pragma unroll
+      for (int e = 0; e < LV; e += 4)
+        *reinterpret_cast<float4*>(ptr + e) = make_float4(get(e), get(e + 1), get(e + 2), get(e + 3));
+    } else if constexpr (V == 2 && sizeof(R) == 4) {
+#pragma unroll
+      for (int e = 0; e < LV; e += 2) *reinterpret_cast<float2*>(ptr + e) = make_float2(get(e), get(e + 1));
+    } else if constexpr (V == 2 && sizeof(R) == 8) {
+#pragma unroll
+      for (int e = 0; e < LV; e += 2) *reinterpret_cast<double2*>(ptr + e) = make_double2(get(e), get(e + 1));
+    } else {
+#pragma unroll
+      for (int e = 0; e < LV; ++e) ptr[e] = get(e);
+    }
+#pragma unroll
+    for (int e = LV; e < L; ++e) ptr[e] = get(e);
+  }
   // strided gather: element i from ptr[i * stride]
   MPCB_DEV void gather(const R* ptr, int stride) {
 #pragma unroll

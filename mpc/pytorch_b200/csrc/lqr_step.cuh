@@ -745,9 +745,10 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
           for (int q = 0; q < M; ++q) Kt[q * VS + cc[sl]] = Kc[sl][q];
         } else {                          // u column: publish Q[:n, n+ua] = Q_xu[:, ua]
-          R* dst = Qx + ua[sl] * VS;
+          Vec<R, N> qxu;                    // rows < n of the control column
 #pragma unroll
-          for (int i = 0; i < N; ++i) dst[i] = Qc[sl].get(i);
+          for (int i = 0; i < N; ++i) qxu.set(i, Qc[sl].get(i));
+          qxu.template store<EA>(Qx + ua[sl] * VS);
         }
       }
     }
@@ -816,9 +817,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
     for (int sl = 0; sl < CPL; ++sl) {
       if (wsl[sl] && isx[sl]) {
         if constexpr (!K::VREG) {
-          R* dst = Vs + cc[sl] * VS;      // column c of V, stored as row c
-#pragma unroll
-          for (int i = 0; i < N; ++i) dst[i] = Vn[sl].get(i);
+          Vn[sl].template store<EA>(Vs + cc[sl] * VS);      // column c of V, stored as row c (vector stores)
         }
         vs[cc[sl]] = vn[sl];
       }
