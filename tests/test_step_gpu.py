@@ -277,3 +277,45 @@ def test_standalone_pnqp_matches_reference_fixture(name):
     assert maxdiff(Hf, Ho) <= (1e-12 if f64 else 1e-6)
     assert maxdiff(x, g["x"]) <= 2e-4                      # reference (batch-coupled) result
     assert torch.equal(If.cpu().bool(), g["If"].bool())    # active set: bit exact
+
+
+def test_bounds_together_with_zero_mask():
+    """u_zero_I given AND box bounds (allowed by the reference: pnqp ignores the mask, the rollout zeroes the
+    masked controls and then clamps them, mpc/lqr_step.py:129-148,197-213)."""
+    B, T, n, m = 7, 6, 4, 2
+    C, c, F, f, x0 = gen_problem(81, B, T, n, m, torch.float64)
+    u, ul, uu = nominal_controls(81, B, T, m, torch.float64, "tensor")
+    g = torch.Generator().manual_seed(4)
+    zI = torch.rand(T, B, m, generator=g) < 0.3
+    x = orc.get_traj(T, u, x0, F, f)
+    o = orc.lqr_step_forward(n, m, T, x0, C, c, F, f, x, u, u_lower=ul, u_upper=uu, u_zero_I=zI, coupled=False)
+    r = raw(n, m, T, x0, C, c, F, f, x, u, u_lower=ul, u_upper=uu, u_zero_I=zI)
+    assert maxdiff(r["new_x"], o.new_x) < 1e-9 and maxdiff(r["new_u"], o.new_u) < 1e-9
+    assert maxdiff(r["costs"], o.costs) < 1e-9 and maxdiff(r["alphas"], o.alphas) == 0.0
+    assert torch.equal(r["free_mask"].bool(), o.free_masks)
+
+
+def test_tensor_bounds_with_delta_u_and_full_length_F():
+    """tensor bounds + trust region, and F carrying T time slices (only F[:T-1] is read, reference
+    mpc/lqr_step.py:66,217-220; dF[T-1] is zero, :387-395)."""
+    from mpc.pytorch_b200 import LQRStep, QuadCost, LinDx
+    B, T, n, m = 5, 6, 3, 2
+    C, c, F, f, x0 = gen_problem(82, B, T, n, m, torch.float64, time_varying=True)
+    FT = torch.cat((F, torch.randn(1, B, n, n + m, dtype=torch.float64)), 0)       # T slices, last one unused
+    u, ul, uu = nominal_controls(82, B, T, m, torch.float64, "tensor")
+    x = orc.get_traj(T, u, x0, F, f)
+    o = orc.lqr_step_forward(n, m, T, x0, C, c, F, f, x, u, u_lower=ul, u_upper=uu, delta_u=0.07, coupled=False)
+    r = raw(n, m, T, x0, C, c, FT, f, x, u, u_lower=ul, u_upper=uu, delta_u=0.07)
+    assert maxdiff(r["new_x"], o.new_x) < 1e-9 and maxdiff(r["new_u"], o.new_u) < 1e-9
+    assert float((r["new_u"] - u).abs().max()) <= 0.07 + 1e-12
+    # gradients with the full-length F: slice T-1 of dF must be exactly zero
+    lv = [t.to(DEV).requires_grad_(True) for t in (x0, C, c, FT, f)]
+    fn = LQRStep(n, m, T, u_lower=cu(ul), u_upper=cu(uu), true_cost=QuadCost(lv[1], lv[2]),
+                 true_dynamics=LinDx(lv[3], lv[4]), current_x=o.new_x.to(DEV), current_u=o.new_u.to(DEV),
+                 no_op_forward=True)
+    xo, uo = fn(*lv)
+    grads = torch.autograd.grad(xo.sum() + (uo * uo).sum(), lv)
+    assert grads[3].shape == FT.shape and float(grads[3][T - 1].abs().max()) == 0.0
+    ref = orc.lqr_step_backward(n, m, T, x0, C, c, F, f, o.new_x, o.new_u, torch.ones_like(o.new_x), 2 * o.new_u,
+                                u_lower=ul, u_upper=uu, coupled=False)
+    assert maxdiff(grads[3][:T - 1], ref[3]) < 1e-9 and maxdiff(grads[0], ref[0]) < 1e-9
