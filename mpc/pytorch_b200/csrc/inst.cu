@@ -3,6 +3,7 @@
 #include "lqr_grad.cuh"
 #include "lqr_rollout.cuh"
 #include "lqr_step.cuh"
+#include "lqr_step2.cuh"
 
 #ifndef INST_N
 #error "compile with -DINST_N=<n_state> -DINST_M=<n_ctrl>"
@@ -13,11 +14,21 @@
 
 namespace mpcb200 {
 
+// a.impl: 0 = pick (the column-pair kernel where its shape constraints hold), 1 = generic kernel, 2 = pair kernel
+template <typename R>
+static int step_dispatch(const StepArgs& a, int max_smem, cudaStream_t s) {
+  if (a.impl != 1) {
+    const int rc = launch_step2<R, INST_N, INST_M>(a, max_smem, s);
+    if (rc >= 0 && !(rc == 4 && a.impl == 0)) return rc;      // rc < 0: shape not supported by the pair mapping
+    if (a.impl == 2 && rc < 0) return 3;
+  }
+  return launch_step<R, INST_N, INST_M>(a, max_smem, s);
+}
 int MPCB_CAT(step_f32_, , INST_N, INST_M)(const StepArgs& a, int max_smem, cudaStream_t s) {
-  return launch_step<float, INST_N, INST_M>(a, max_smem, s);
+  return step_dispatch<float>(a, max_smem, s);
 }
 int MPCB_CAT(step_f64_, , INST_N, INST_M)(const StepArgs& a, int max_smem, cudaStream_t s) {
-  return launch_step<double, INST_N, INST_M>(a, max_smem, s);
+  return step_dispatch<double>(a, max_smem, s);
 }
 int MPCB_CAT(grad_f32_, , INST_N, INST_M)(const GradArgs& a, cudaStream_t s) {
   return launch_grad<float, INST_N, INST_M>(a, s);

@@ -51,6 +51,7 @@ struct StepArgs {
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
   int debug;      // developer experiments (env MPCB200_DEBUG): 1 = no data movement, 2 = no math
+  int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh)
 };
 
 template <typename R, int N, int M>

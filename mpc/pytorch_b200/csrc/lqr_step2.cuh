@@ -1,0 +1,747 @@
+// lqr_step2.cuh - the box-constrained LQR step, column-PAIR mapping with self-feeding warps (sm_100a).
+//
+// Same contract as lqr_step.cuh (reference LQRStepFn.forward, mpc/lqr_step.py:277-309: c_back :289-295,
+// lqr_backward :52-160 incl. pnqp mpc/pnqp.py:5-82 and the u_zero_I solve :100-127, lqr_forward :164-261),
+// different machine mapping.  Why a second mapping: the round-1 kernel (one column per lane) issues one
+// shared-memory operand per FMA - 79 LSU wavefronts per problem-step at config 3 - and spends 20 % of its
+// instructions polling mbarriers between a producer warp and its consumers.  Here
+//  * L = (n+m)/2 lanes own one problem; a lane owns the column PAIR (c0, c0+1) of Q_t, F_t, C_t (x lanes also
+//    the pair of V and K_t columns).  Every value a lane loads from shared memory feeds two FMAs of ONE packed
+//    FFMA2 (pair x broadcast scalar), so operands per FMA halve and 32/L problems share a warp
+//    (n=8, m=2: 6 problems / warp instead of 3).
+//  * no producer warp and no empty barriers: every warp streams its OWN tiles.  After a warp has consumed
+//    stage s, up to 8 of its lanes each issue one 1-D bulk TMA copy (C, F, c, x_bar, u_bar, f, bounds) of tile
+//    seq+S into that stage in ONE instruction; completion is an mbarrier transaction count.  Warps are
+//    independent (a CTA is just NW of them), so the CTA size is only a scheduling granularity.
+//  * V is exchanged through a per-problem row-major buffer (a lane stores its column pair of every row with
+//    8-byte stores, readers take whole rows as broadcast 128-bit loads) - exact V, no symmetry assumption.
+//  * gains K_t, k_t of all T steps stay in shared memory (or the caller's Ks/ks for long horizons); the
+//    rollout keeps the state replicated in every lane, lane pairs compute their two rows of F tau and C tau.
+// Shapes: n and m even and the per-warp spans 16-byte aligned (Step2Cfg::OK); everything else runs the
+// generic kernel in lqr_step.cuh.
+#pragma once
+#include "lqr_step.cuh"
+
+#ifndef MPCB2_STAGES
+#define MPCB2_STAGES 3
+#endif
+#ifndef MPCB2_NW
+#define MPCB2_NW 1
+#endif
+
+namespace mpcb200 {
+
+template <typename R>
+MPCB_DEV P2<R> ld_pair(const R* p);
+template <>
+MPCB_DEV P2<float> ld_pair<float>(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return {v.x, v.y};
+}
+template <>
+MPCB_DEV P2<double> ld_pair<double>(const double* p) {
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  return {v.x, v.y};
+}
+MPCB_DEV void st_pair(float* p, P2<float> v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+MPCB_DEV void st_pair(double* p, P2<double> v) { *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y); }
+// a * (s, s) + c
+template <typename R>
+MPCB_DEV P2<R> fma2s(P2<R> a, R s, P2<R> c) { return fma2(a, P2<R>{s, s}, c); }
+
+// Load CNT contiguous elements whose address is aligned to A elements (A a power of two): widest vector
+// loads first (at most 16 bytes), narrower ones for the remainder.
+template <typename R, int CNT, int A>
+MPCB_DEV void load_span(const R* p, R (&out)[CNT]) {
+  constexpr int EA = 16 / (int)sizeof(R);
+  constexpr int W = A < EA ? A : EA;
+  constexpr int NV = (CNT / W) * W;
+  if constexpr (NV > 0) {
+#pragma unroll
+    for (int e = 0; e < NV; e += W) VecLoad<R, W>::ld(p + e, &out[e]);
+  }
+  if constexpr (NV < CNT) {
+    if constexpr (W >= 2) {
+      R rest[CNT - NV];
+      load_span<R, CNT - NV, W / 2>(p + NV, rest);
+#pragma unroll
+      for (int e = 0; e < CNT - NV; ++e) out[NV + e] = rest[e];
+    } else {
+#pragma unroll
+      for (int e = NV; e < CNT; ++e) out[e] = p[e];
+    }
+  }
+}
+// sum_i a[i] b[i] with packed pair FMAs (even/odd partial sums, one final add); CNT even
+template <typename R, int CNT>
+MPCB_DEV R dot_span(const R (&a)[CNT], const R (&b)[CNT]) {
+  static_assert(CNT % 2 == 0, "pairs");
+  P2<R> acc = mul2(P2<R>{a[0], a[1]}, P2<R>{b[0], b[1]});
+#pragma unroll
+  for (int k = 2; k < CNT; k += 2) acc = fma2(P2<R>{a[k], a[k + 1]}, P2<R>{b[k], b[k + 1]}, acc);
+  return acc.x + acc.y;
+}
+
+template <typename R, int N, int M>
+struct Step2Cfg {
+  static constexpr int P = N + M;
+  static constexpr int L = P / 2;            // lanes per problem
+  static constexpr int NXL = N / 2;          // x lanes (own two state columns each)
+  static constexpr int PPW = L > 0 ? 32 / (L > 0 ? L : 1) : 1;   // problems per warp
+  static constexpr int S = MPCB2_STAGES;
+  static constexpr int NW = MPCB2_NW;        // independent warps per CTA
+  static constexpr int EA = 16 / (int)sizeof(R);
+  static constexpr int SZ = (int)sizeof(R);
+  // shapes this mapping supports: even n, m; per-warp spans of every tensor 16-byte multiples
+  static constexpr bool OK = (N % 2 == 0) && (M % 2 == 0) && L <= 16 && (PPW * M * SZ) % 16 == 0 &&
+                             (PPW * N * SZ) % 16 == 0 && (PPW * P * SZ) % 16 == 0;
+  // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
+  static constexpr int OFF_C = 0;
+  static constexpr int OFF_F = OFF_C + PPW * P * P;
+  static constexpr int OFF_c = OFF_F + PPW * N * P;
+  static constexpr int OFF_x = OFF_c + PPW * P;
+  static constexpr int OFF_u = OFF_x + PPW * N;
+  static constexpr int OFF_f = OFF_u + PPW * M;
+  static constexpr int OFF_lo = OFF_f + PPW * N;
+  static constexpr int OFF_hi = OFF_lo + PPW * M;
+  static constexpr int OFF_END = OFF_hi + PPW * M;
+  static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
+  // per-problem scratch (elements); strides chosen so the PPW problems of a warp hit distinct 16-byte bank groups
+  static constexpr int NV = round_up(N, 4);             // row stride of V / K rows (16-byte aligned rows)
+  static constexpr int VSTR = NV;
+  static constexpr int SC_V = 0;                         // N x NV value matrix, row-major
+  static constexpr int SC_v = SC_V + N * VSTR;           // NV
+  static constexpr int SC_Q = SC_v + NV;                 // N x M   Q_xu, row-major [i][a]
+  static constexpr int SC_X = SC_Q + round_up(N * M, 4); // 2 x NV  rollout state exchange
+  static constexpr int SC_R = SC_X + 2 * NV;             // L       cost reduction
+  static constexpr int SC_K = SC_R + round_up(L, 4);     // M x NV + M gain exchange when gains are not smem resident
+  static constexpr int KT = M * NV + round_up(M, 4);     // elements per (problem, t) of the gain store
+  static constexpr int SC_RAW = SC_K + KT;
+  // guaranteed alignment (elements) of per-problem spans inside a stage
+  static constexpr int A_N = align_elems<R>(N), A_M = align_elems<R>(M), A_P = align_elems<R>(P);
+  static constexpr int pick_scr() {
+    // smallest stride >= SC_RAW, multiple of 4, with (stride % 32) in {4, 12, 20, 28}: consecutive problems
+    // then start 4 banks apart (mod 32) and broadcast 128-bit loads of up to 8 problems never collide
+    int s = round_up(SC_RAW, 4);
+    while (s % 8 != 4) s += 4;
+    return s;
+  }
+  static constexpr int SCRS = pick_scr();
+  static constexpr int HDR_BYTES = 128;                  // S mbarriers (per warp)
+  __host__ __device__ static size_t warp_smem_bytes(int T, bool k_in_smem) {
+    size_t b = HDR_BYTES + (size_t)S * STAGE_BYTES + (size_t)PPW * SCRS * SZ;
+    if (k_in_smem) b += (size_t)PPW * T * KT * SZ;
+    return round_up((int)b, 128);
+  }
+  static size_t smem_bytes(int T, bool k_in_smem) { return (size_t)NW * warp_smem_bytes(T, k_in_smem); }
+};
+
+
+// Synchronous tile copy for shapes / tails the bulk path cannot take (spans not 16-byte aligned): plain loads
+// by the whole warp, no prefetch.  Kept out of line: it is never on the hot path.
+template <typename R, int N, int M>
+__device__ __noinline__ void tile_copy_sync(const void* gC, const void* gF, const void* gc, const void* gx, const void* gu,
+                                            const void* gf, const void* glo, const void* ghi, int B, int T, R* st, int t,
+                                            bool needf, int b0, int cnt, int lane) {
+  using K = Step2Cfg<R, N, M>;
+  constexpr int P = K::P;
+  const size_t tb = (size_t)t * B + b0;
+  auto cp = [&](int off, const void* src, int per) {
+    const R* g = (const R*)src + tb * per;
+#pragma unroll 1
+    for (int i = lane; i < cnt * per; i += 32) st[off + i] = g[i];
+  };
+  cp(K::OFF_C, gC, P * P);
+  if (t < T - 1) cp(K::OFF_F, gF, N * P);
+  cp(K::OFF_c, gc, P);
+  cp(K::OFF_x, gx, N);
+  cp(K::OFF_u, gu, M);
+  if (needf) cp(K::OFF_f, gf, N);
+  if (glo != nullptr) {
+    cp(K::OFF_lo, glo, M);
+    cp(K::OFF_hi, ghi, M);
+  }
+}
+
+#ifdef MPCB2_TIMING
+#define TICK2(arr, i) { ck1 = clock64(); arr[i] += ck1 - ck0; ck0 = ck1; }
+#else
+#define TICK2(arr, i)
+#endif
+
+template <typename R, int N, int M, int MODE>
+__global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32)
+lqr_step2_kernel(const StepArgs a) {
+  using K = Step2Cfg<R, N, M>;
+  constexpr int P = K::P, L = K::L, NXL = K::NXL, PPW = K::PPW, S = K::S, SZ = K::SZ, KT = K::KT, VSTR = K::VSTR, NV = K::NV;
+  constexpr int EA = K::EA, A_N = K::A_N, A_M = K::A_M;
+  constexpr unsigned FULLM = (1u << M) - 1u;
+  constexpr bool BOX = MODE == MODE_BOX;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = K::NW == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int T = a.T, B = a.B;
+  const int gw = blockIdx.x * K::NW + warp;                 // global warp index
+  const int b0 = gw * PPW;
+  if (b0 >= B) return;                                      // warps are independent: no CTA-wide barrier below
+  const int cnt = min(PPW, B - b0);
+  unsigned char* wbase = smem_raw + (size_t)warp * K::warp_smem_bytes(T, a.k_in_smem != 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(wbase);
+  unsigned char* stage_base = wbase + K::HDR_BYTES;
+  R* scratch = reinterpret_cast<R*>(stage_base + (size_t)S * K::STAGE_BYTES);
+  R* kstore = scratch + (size_t)PPW * K::SCRS;
+
+  const bool writer_lane = lane < PPW * L;
+  const int pi = writer_lane ? lane / L : PPW - 1;
+  const int base = pi * L;
+  const int lq = writer_lane ? lane - base : L - 1;
+  const int b = b0 + pi;
+  const bool valid = b < B;
+  const bool wr = writer_lane && valid;
+  const bool isx = lq < NXL;
+  const int c0 = 2 * lq;                                    // first owned column (x then u columns)
+  const int ua0 = isx ? 0 : c0 - N;                         // first owned control (u lanes)
+  const int xr0 = isx ? c0 : 0;                             // a valid state row for every lane
+
+  // ------------------------------------------------------------------ tile streaming (this warp's own ring)
+  const bool tail_ok = (cnt == PPW) || (((cnt * M * SZ) % 16 == 0) && ((cnt * N * SZ) % 16 == 0) &&
+                                        ((cnt * P * SZ) % 16 == 0));
+  const bool bulk = a.bulk_ok && tail_ok;
+  // tile streaming: warp-uniform addresses, lane 0 issues one 1-D bulk copy per tensor
+  const size_t e0 = (size_t)b0;
+  const char* pC = (const char*)a.C + e0 * (P * P) * SZ;
+  const char* pF = (const char*)a.F + e0 * (N * P) * SZ;
+  const char* pc = (const char*)a.c + e0 * P * SZ;
+  const char* px = (const char*)a.cur_x + e0 * N * SZ;
+  const char* pu = (const char*)a.cur_u + e0 * M * SZ;
+  const char* pf = (const char*)a.f + e0 * N * SZ;
+  const char* plo = (const char*)a.u_lower + e0 * M * SZ;
+  const char* phi = (const char*)a.u_upper + e0 * M * SZ;
+  const uint32_t ucnt = (uint32_t)cnt;
+  const uint32_t by_base = ucnt * (P * P + P + N + M) * SZ + (a.bounds_kind == 2 ? 2u * ucnt * M * SZ : 0u);
+  const uint32_t by_F = ucnt * N * P * SZ, by_f = ucnt * N * SZ;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  int iss = 0;                                              // tiles issued so far (stage = iss % S)
+  auto issue = [&](int t, bool fwd) {
+    if (bulk) {
+      const int s = iss % S;
+      const bool needF = t < T - 1;
+      const bool needf = fwd && needF && a.has_f;
+      if (lane == 0) {
+        unsigned char* dst = stage_base + (size_t)s * K::STAGE_BYTES;
+        uint64_t* bar = &full[s];
+        const size_t tB = (size_t)t * B;
+        mbar_arrive_expect_tx(bar, by_base + (needF ? by_F : 0u) + (needf ? by_f : 0u));
+        bulk_g2s(dst + K::OFF_C * SZ, pC + tB * (P * P) * SZ, ucnt * (P * P) * SZ, bar);
+        if (needF) bulk_g2s(dst + K::OFF_F * SZ, pF + tB * (N * P) * SZ, by_F, bar);
+        bulk_g2s(dst + K::OFF_c * SZ, pc + tB * P * SZ, ucnt * P * SZ, bar);
+        bulk_g2s(dst + K::OFF_x * SZ, px + tB * N * SZ, ucnt * N * SZ, bar);
+        bulk_g2s(dst + K::OFF_u * SZ, pu + tB * M * SZ, ucnt * M * SZ, bar);
+        if (needf) bulk_g2s(dst + K::OFF_f * SZ, pf + tB * N * SZ, by_f, bar);
+        if (a.bounds_kind == 2) {
+          bulk_g2s(dst + K::OFF_lo * SZ, plo + tB * M * SZ, ucnt * M * SZ, bar);
+          bulk_g2s(dst + K::OFF_hi * SZ, phi + tB * M * SZ, ucnt * M * SZ, bar);
+        }
+      }
+    }
+    ++iss;
+  };
+  int con = 0;                                              // tiles consumed so far
+  // wait for tile `con` (bulk) or copy it synchronously (unaligned shapes / tails); returns the stage pointer
+  auto acquire = [&](int t, bool fwd) -> const R* {
+    const int s = con % S;
+    R* st = (R*)(stage_base + (size_t)s * K::STAGE_BYTES);
+    if (bulk) {
+      mbar_wait(&full[s], (uint32_t)((con / S) & 1));
+    } else {
+      tile_copy_sync<R, N, M>(a.C, a.F, a.c, a.cur_x, a.cur_u, a.f, a.bounds_kind == 2 ? a.u_lower : nullptr, a.u_upper, B, T,
+                              st, t, fwd && t < T - 1 && a.has_f, b0, cnt, lane);
+      __syncwarp();
+    }
+    ++con;
+    return st;
+  };
+  // global tile sequence of the sweep + first rollout pass: g < T -> (T-1-g, backward), else (g-T, forward)
+  const int G = T + (a.do_rollout ? T : 0);
+  auto issue_g = [&](int g) {
+    if (g < T) issue(T - 1 - g, false);
+    else issue(g - T, true);
+  };
+  for (int g = 0; g < S && g < G; ++g) issue_g(g);
+
+  // per-problem element offsets inside a stage
+  const int oC = K::OFF_C + pi * P * P, oF = K::OFF_F + pi * N * P;
+  const int oc = K::OFF_c + pi * P, of_ = K::OFF_f + pi * N, ox = K::OFF_x + pi * N, ou = K::OFF_u + pi * M;
+  const int olo = K::OFF_lo + pi * M, ohi = K::OFF_hi + pi * M;
+  R* scr = scratch + (size_t)pi * K::SCRS;
+  R* Vs = scr + K::SC_V;
+  R* vs = scr + K::SC_v;
+  R* Qx = scr + K::SC_Q;
+  R* xs = scr + K::SC_X;
+  R* red = scr + K::SC_R;
+  R* kst = a.k_in_smem ? kstore + (size_t)pi * T * KT : scr + K::SC_K;
+  R* gKs = (R*)a.Ks;
+  R* gks = (R*)a.ks;
+  const R s_lo = (R)a.u_lo, s_hi = (R)a.u_hi, s_du = (R)a.delta_u, decay = (R)a.ls_decay;
+  const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
+  const int bsafe = valid ? b : B - 1;
+
+  unsigned status = 0u;
+  R oldcost_part = R(0);
+  R kprev[M];
+#pragma unroll
+  for (int q = 0; q < M; ++q) kprev[q] = R(0);
+#ifdef MPCB2_TIMING
+  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tf[6] = {0, 0, 0, 0, 0, 0};
+  long long ck0, ck1;
+#endif
+
+  // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
+  for (int t = T - 1; t >= 0; --t) {
+#ifdef MPCB2_TIMING
+    ck0 = clock64();
+#endif
+    const R* st = acquire(t, false);
+    TICK2(tk, 0)
+    // zero-mask bytes of this (t, problem): tiny, read straight from global
+    unsigned zm = 0u;
+    if (has_mask) {
+#pragma unroll
+      for (int q = 0; q < M; ++q) zm |= (a.zero_mask[((size_t)t * B + bsafe) * M + q] ? 1u : 0u) << q;
+    }
+    // nominal point tau_bar replicated on every lane
+    R tb[P];
+    {
+      R tx[N], tu[M];
+      load_span<R, N, A_N>(st + ox, tx);
+      load_span<R, M, A_M>(st + ou, tu);
+#pragma unroll
+      for (int i = 0; i < N; ++i) tb[i] = tx[i];
+#pragma unroll
+      for (int q = 0; q < M; ++q) tb[N + q] = tu[q];
+    }
+    // owned column pair of C_t and F_t; rows c0, c0+1 of C_t for c_back = C tau_bar + c (lqr_step.py:289-295)
+    P2<R> Qp[P];                                   // (Q[i][c0], Q[i][c0+1])
+#pragma unroll
+    for (int i = 0; i < P; ++i) Qp[i] = ld_pair<R>(st + oC + i * P + c0);
+    P2<R> qp;
+    {
+      R Cr0[P], Cr1[P];
+      load_span<R, P, EA>(st + oC + c0 * P, Cr0);          // c0 * P is a multiple of 4
+      load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
+      const R ct0 = dot_span<R, P>(Cr0, tb), ct1 = dot_span<R, P>(Cr1, tb);
+      const P2<R> cj = ld_pair<R>(st + oc + c0);
+      const P2<R> tj = ld_pair<R>(st + (isx ? ox + c0 : ou + ua0));
+      if (writer_lane) oldcost_part += tj.x * (R(0.5) * ct0 + cj.x) + tj.y * (R(0.5) * ct1 + cj.y);   // util.get_cost (:169)
+      qp = {ct0 + cj.x, ct1 + cj.y};
+    }
+    TICK2(tk, 1)
+    if (t < T - 1) {                               // Q = C + F'VF, q = c_back + F'v  (:66-70)
+      P2<R> Fp[N];                                 // (F[k][c0], F[k][c0+1])
+#pragma unroll
+      for (int k = 0; k < N; ++k) Fp[k] = ld_pair<R>(st + oF + k * P + c0);
+      P2<R> Wp[N];                                 // (W[i][c0], W[i][c0+1]),  W = V F
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        R Vr[N];
+        load_span<R, N, EA>(Vs + i * VSTR, Vr);
+        Wp[i] = {R(0), R(0)};
+#pragma unroll
+        for (int k = 0; k < N; ++k) Wp[i] = fma2s(Fp[k], Vr[k], Wp[i]);
+      }
+      // Q[:, pair] += F' W[:, pair]: rows of F come as 2-row chunks of the flat tile (16-byte aligned)
+#pragma unroll
+      for (int k = 0; k < N; k += 2) {
+        R Fr[2 * P];
+        load_span<R, 2 * P, EA>(st + oF + k * P, Fr);     // k even: k * P is a multiple of 4
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          Qp[i] = fma2s(Wp[k], Fr[i], Qp[i]);
+          Qp[i] = fma2s(Wp[k + 1], Fr[P + i], Qp[i]);
+        }
+      }
+      R vv[N];
+      load_span<R, N, EA>(vs, vv);
+#pragma unroll
+      for (int k = 0; k < N; ++k) qp = fma2s(Fp[k], vv[k], qp);
+    }
+    TICK2(tk, 2)
+    // replicate Q_uu, q_u: control column a lives in lane base + NXL + a/2, component a%2
+    R Quu[M][M], qu[M];
+#pragma unroll
+    for (int a2 = 0; a2 < M; ++a2) {
+      const int src = base + NXL + a2 / 2;
+#pragma unroll
+      for (int p1 = 0; p1 < M; ++p1) Quu[p1][a2] = shfl((a2 & 1) ? Qp[N + p1].y : Qp[N + p1].x, src);
+      qu[a2] = shfl((a2 & 1) ? qp.y : qp.x, src);
+    }
+    TICK2(tk, 3)
+    R kk[M];
+    unsigned fm = FULLM;
+    int it = 0;
+    Ldl<R, M> fac;
+    if constexpr (BOX) {                           // (:129-148)
+      R lb[M], ub[M];
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        const R lo_abs = a.bounds_kind == 2 ? st[olo + q] : s_lo;
+        const R hi_abs = a.bounds_kind == 2 ? st[ohi + q] : s_hi;
+        const R ubq = tb[N + q];
+        lb[q] = lo_abs - ubq;
+        ub[q] = hi_abs - ubq;
+        if (a.has_delta) {
+          if (lb[q] < -s_du) lb[q] = -s_du;
+          if (ub[q] > s_du) ub[q] = s_du;
+        }
+        kk[q] = kprev[q];
+      }
+      if (!valid) {   // padding problems of a tail warp compute on stale shared memory: give their
+                      // (data dependent) pnqp loop a trivial QP so they never become the slowest problem
+#pragma unroll
+        for (int p1 = 0; p1 < M; ++p1) {
+#pragma unroll
+          for (int p2 = 0; p2 < M; ++p2) Quu[p1][p2] = p1 == p2 ? R(1) : R(0);
+          qu[p1] = R(0);
+          lb[p1] = R(-1);
+          ub[p1] = R(1);
+          kk[p1] = R(0);
+        }
+      }
+      bool conv, badpiv;
+      pnqp_lane<R, M>(Quu, qu, lb, ub, t < T - 1, kk, fac, fm, it, conv, badpiv, a.pnqp_iters);
+      if (!conv) status |= 1u;
+      if (badpiv) status |= 4u;
+#pragma unroll
+      for (int q = 0; q < M; ++q) kprev[q] = kk[q];
+    } else {                                       // unconstrained (:84-94) or u_zero_I masked (:100-127)
+      if constexpr (MODE == MODE_MASK) fm = FULLM & ~zm;
+      R A[M][M], rhs[M], sol[M];
+#pragma unroll
+      for (int p1 = 0; p1 < M; ++p1) {
+        const bool f1 = (fm >> p1) & 1u;
+        rhs[p1] = f1 ? qu[p1] : R(0);
+#pragma unroll
+        for (int p2 = 0; p2 < M; ++p2) A[p1][p2] = (f1 && ((fm >> p2) & 1u)) ? Quu[p1][p2] : R(0);
+        if (!f1) A[p1][p1] += R(1e-8);
+      }
+      fac.factor(A);
+      if (fac.bad) status |= 4u;
+      fac.solve(rhs, sol);
+#pragma unroll
+      for (int q = 0; q < M; ++q) kk[q] = -sol[q];
+    }
+    TICK2(tk, 4)
+    // K[:, pair] = -Hff^{-1} Qux_f[:, pair] (rows of clamped / masked controls are zero)
+    P2<R> Kp[M];
+    R* Kt = a.k_in_smem ? kst + (size_t)t * KT : kst;
+    {
+      R r0[M], r1[M], s0[M], s1[M];
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        const bool fq = (fm >> q) & 1u;
+        r0[q] = fq ? Qp[N + q].x : R(0);
+        r1[q] = fq ? Qp[N + q].y : R(0);
+      }
+      fac.solve(r0, s0);
+      fac.solve(r1, s1);
+#pragma unroll
+      for (int q = 0; q < M; ++q) Kp[q] = {-s0[q], -s1[q]};
+    }
+    if (writer_lane) {
+      if (isx) {
+#pragma unroll
+        for (int q = 0; q < M; ++q) st_pair(Kt + q * NV + c0, Kp[q]);
+        if (lq == 0) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) Kt[M * NV + q] = kk[q];
+        }
+      } else {                                     // u lane: publish Q_xu[:, pair] as rows [i][a]
+#pragma unroll
+        for (int i = 0; i < N; ++i) st_pair(Qx + i * M + ua0, Qp[i]);
+      }
+    }
+    if (wr) {
+      const size_t tbo = (size_t)t * B + b;
+      if (gKs != nullptr && isx) {
+#pragma unroll
+        for (int q = 0; q < M; ++q) st_pair(gKs + (tbo * M + q) * N + c0, Kp[q]);
+        if (lq == 0) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) gks[tbo * M + q] = kk[q];
+        }
+      }
+      if (lq == 0) {
+        if (BOX && a.qp_iters != nullptr) a.qp_iters[tbo] = it;
+        if (a.free_mask != nullptr) {
+#pragma unroll
+          for (int q = 0; q < M; ++q) a.free_mask[tbo * M + q] = (fm >> q) & 1u;
+        }
+      }
+    }
+    __syncwarp();
+    TICK2(tk, 5)
+    // V = Qxx + Qxu K + K'Qux + K'Quu K ; v = qx + Qxu k + K'qu + K'Quu k   (:155-158)
+    {
+      P2<R> Gp[M];                                 // (Qux + Quu K)[a][pair]
+      R gq[M];                                     // qu + Quu k
+#pragma unroll
+      for (int p1 = 0; p1 < M; ++p1) {
+        Gp[p1] = Qp[N + p1];
+        gq[p1] = qu[p1];
+#pragma unroll
+        for (int p2 = 0; p2 < M; ++p2) {
+          Gp[p1] = fma2s(Kp[p2], Quu[p1][p2], Gp[p1]);
+          gq[p1] += Quu[p1][p2] * kk[p2];
+        }
+      }
+      R Qf[N * M];                                 // Q_xu flat [i][a]
+      load_span<R, N * M, EA>(Qx, Qf);
+      R Kr[M][N];
+#pragma unroll
+      for (int q = 0; q < M; ++q) load_span<R, N, EA>(Kt + q * NV, Kr[q]);
+      P2<R> Vp[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        Vp[i] = Qp[i];
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          Vp[i] = fma2s(Kp[q], Qf[i * M + q], Vp[i]);
+          Vp[i] = fma2s(Gp[q], Kr[q][i], Vp[i]);
+        }
+      }
+      P2<R> vp = qp;
+      {
+        R qa[2 * M];                               // Q_xu rows c0, c0+1 (x lanes; any valid rows otherwise)
+        load_span<R, 2 * M, (2 * M) % 4 == 0 ? 4 : 2>(Qx + xr0 * M, qa);
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          vp.x += qa[q] * kk[q];
+          vp.y += qa[M + q] * kk[q];
+          vp = fma2s(Kp[q], gq[q], vp);
+        }
+      }
+      if (writer_lane && isx) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) st_pair(Vs + i * VSTR + c0, Vp[i]);
+        st_pair(vs + c0, vp);
+      }
+    }
+    TICK2(tk, 6)
+    __syncwarp();
+    {
+      const int g = (T - 1 - t) + S;
+      if (g < G) issue_g(g);
+    }
+    TICK2(tk, 7)
+  }
+
+  // nominal cost (sum of the lanes' partial sums, fixed order)
+  if (writer_lane) red[lq] = oldcost_part;
+  __syncwarp();
+  R oldcost = R(0);
+#pragma unroll
+  for (int i = 0; i < L; ++i) oldcost += red[i];
+  __syncwarp();
+
+  if (!a.do_rollout) {
+    if (wr && lq == 0 && a.status != nullptr) a.status[b] = (int)status;
+    return;
+  }
+
+  // ======================= rollout + line search (lqr_step.py:164-261) =======================
+  const R* gx0 = (const R*)a.x_init;
+  R* gnx = (R*)a.new_x;
+  R* gnu = (R*)a.new_u;
+  R* gdu1 = (R*)a.du_first;
+  R alpha = R(1), fdn = R(0), cost = R(0);
+  bool worse = false;
+  for (int pass = 0;; ++pass) {
+    if (pass > 0) {                                // line-search repeat: restart this warp's tile stream
+      for (int g = 0; g < S && g < T; ++g) issue(g, true);
+    }
+    R xr[N];                                       // state replicated on every lane
+#pragma unroll
+    for (int i = 0; i < N; ++i) xr[i] = gx0[(size_t)bsafe * N + i];
+    P2<R> xown = {gx0[(size_t)bsafe * N + xr0], gx0[(size_t)bsafe * N + xr0 + 1]};
+    R cpart = R(0), dun2 = R(0);
+    size_t orow = (size_t)bsafe;                   // t*B + b
+    for (int t = 0; t < T; ++t, orow += (size_t)B) {
+#ifdef MPCB2_TIMING
+      ck0 = clock64();
+#endif
+      const R* st = acquire(t, true);
+      TICK2(tf, 0)
+      unsigned zm = 0u;
+      if (has_mask) {
+#pragma unroll
+        for (int q = 0; q < M; ++q) zm |= (a.zero_mask[orow * M + q] ? 1u : 0u) << q;
+      }
+      R xb[N], ubar[M];
+      load_span<R, N, A_N>(st + ox, xb);
+      load_span<R, M, A_M>(st + ou, ubar);
+      R dxv[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) dxv[i] = xr[i] - xb[i];
+      R u[M];
+      {
+        const R* Kt = a.k_in_smem ? kst + (size_t)t * KT : nullptr;
+        const R* Kg = gKs + orow * M * N;
+        const R* kg = gks + orow * M;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          R Krow[N];
+          R kq;
+          if (a.k_in_smem) {
+            load_span<R, N, EA>(Kt + q * NV, Krow);
+            kq = Kt[M * NV + q];
+          } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) Krow[i] = __ldcg(Kg + q * N + i);
+            kq = __ldcg(kg + q);
+          }
+          u[q] = (dot_span<R, N>(Krow, dxv) + ubar[q]) + alpha * kq;          // (:192)
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        if constexpr (MODE != MODE_PLAIN) {
+          if (has_mask && ((zm >> q) & 1u)) u[q] = R(0);                     // (:197-198)
+        }
+        if constexpr (BOX) {                                                // (:200-213)
+          R lo = a.bounds_kind == 2 ? st[olo + q] : s_lo;
+          R hi = a.bounds_kind == 2 ? st[ohi + q] : s_hi;
+          if (a.has_delta) {
+            const R l2 = ubar[q] - s_du, h2 = ubar[q] + s_du;
+            lo = l2 < lo ? lo : l2;
+            hi = h2 > hi ? hi : h2;
+          }
+          u[q] = u[q] < lo ? lo : u[q];                                       // util.eclamp: lower, then upper
+          u[q] = u[q] > hi ? hi : u[q];
+        }
+        const R d = ubar[q] - u[q];
+        dun2 += d * d;
+      }
+      TICK2(tf, 1)
+      R tau[P];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tau[i] = xr[i];
+#pragma unroll
+      for (int q = 0; q < M; ++q) tau[N + q] = u[q];
+      // own pair of tau: x lanes carry it, u lanes pick their controls
+      P2<R> tj = xown;
+      if (!isx) {
+#pragma unroll
+        for (int q = 0; q < M; q += 2)
+          if (q == ua0) tj = {u[q], u[q + 1]};
+      }
+      {
+        R Cr0[P], Cr1[P];
+        load_span<R, P, EA>(st + oC + c0 * P, Cr0);
+        load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
+        const P2<R> cj = ld_pair<R>(st + oc + c0);
+        if (writer_lane)
+          cpart += tj.x * (R(0.5) * dot_span<R, P>(Cr0, tau) + cj.x) + tj.y * (R(0.5) * dot_span<R, P>(Cr1, tau) + cj.y);   // (:232)
+      }
+      if (wr) {
+        if (isx) {
+          st_pair(gnx + orow * N + c0, tj);
+        } else {
+          st_pair(gnu + orow * M + ua0, tj);
+          if (pass == 0 && gdu1 != nullptr) {
+            const P2<R> ub2 = ld_pair<R>(st + ou + ua0);
+            st_pair(gdu1 + orow * M + ua0, P2<R>{ub2.x - tj.x, ub2.y - tj.y});
+          }
+        }
+      }
+      TICK2(tf, 2)
+      if (t < T - 1) {                                                        // (:217-222)
+        R Fr0[P], Fr1[P];
+        load_span<R, P, EA>(st + oF + xr0 * P, Fr0);
+        load_span<R, P, 2>(st + oF + (xr0 + 1) * P, Fr1);
+        P2<R> xn = {dot_span<R, P>(Fr0, tau), dot_span<R, P>(Fr1, tau)};
+        if (a.has_f) {
+          const P2<R> fj = ld_pair<R>(st + of_ + xr0);
+          xn.x += fj.x;
+          xn.y += fj.y;
+        }
+        R* xsb = xs + (t & 1) * NV;
+        if (writer_lane && isx) st_pair(xsb + c0, xn);
+        xown = xn;
+        __syncwarp();
+        load_span<R, N, EA>(xsb, xr);
+      }
+      TICK2(tf, 3)
+      __syncwarp();
+      if (t + S < T) issue(t + S, true);
+      TICK2(tf, 4)
+    }
+    if (writer_lane) red[lq] = cpart;
+    __syncwarp();
+    cost = R(0);
+#pragma unroll
+    for (int i = 0; i < L; ++i) cost += red[i];
+    __syncwarp();
+    if (pass == 0) fdn = sqrt(dun2);                                          // (:243-245)
+    worse = cost > oldcost;
+    const bool more = pass + 1 < a.max_ls;
+    if (worse) alpha *= decay;                                                // (:247)
+    const bool again = __any_sync(0xffffffffu, wr && worse) && more;          // per problem == the reference's batch loop
+    if (!again) break;
+  }
+#ifdef MPCB2_TIMING
+  if (lane == 0 && (gw % 97) == 0)
+    printf("warp %d T=%d bwd/step: wait %lld pre %lld WQ %lld shfl %lld solve %lld Kexch %lld Vupd %lld issue %lld | fwd/step: wait %lld u %lld cost %lld dyn %lld issue %lld\n",
+           gw, T, tk[0] / T, tk[1] / T, tk[2] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T, tk[7] / T,
+           tf[0] / T, tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
+#endif
+  if (worse) alpha /= decay;                                                  // (:252)
+  if (wr && lq == 0) {
+    ((R*)a.costs)[b] = cost;
+    ((R*)a.full_du_norm)[b] = fdn;
+    ((R*)a.alphas)[b] = alpha;
+    if (!(cost - cost == R(0))) status |= 2u;
+    if (a.status != nullptr) a.status[b] = (int)status;
+  }
+}
+
+template <typename R, int N, int M, int MODE>
+int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
+  using K = Step2Cfg<R, N, M>;
+  StepArgs a = args;
+  a.k_in_smem = 1;
+  size_t smem = K::smem_bytes(a.T, true);
+  const bool have_ws = a.Ks != nullptr && a.ks != nullptr;
+  // keep a few warps per SM resident: move the gain store to the caller's buffer when it is what limits them
+  const bool crowded = K::warp_smem_bytes(a.T, true) > (size_t)max_smem_optin / 6;
+  if (smem > (size_t)max_smem_optin || (crowded && have_ws && a.do_rollout)) {
+    a.k_in_smem = 0;
+    smem = K::smem_bytes(a.T, false);
+    if (smem > (size_t)max_smem_optin) return 4;
+    if (a.do_rollout && !have_ws) return 4;
+  }
+  auto kern = lqr_step2_kernel<R, N, M, MODE>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
+  const int warps = (a.B + K::PPW - 1) / K::PPW;
+  const int grid = (warps + K::NW - 1) / K::NW;
+  kern<<<grid, K::NW * 32, smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 5;
+}
+
+template <typename R, int N, int M>
+int launch_step2(const StepArgs& a, int max_smem_optin, cudaStream_t stream) {
+  if constexpr (Step2Cfg<R, N, M>::OK) {
+    if (a.bounds_kind != 0) return launch_step2_mode<R, N, M, MODE_BOX>(a, max_smem_optin, stream);
+    if (a.has_mask) return launch_step2_mode<R, N, M, MODE_MASK>(a, max_smem_optin, stream);
+    return launch_step2_mode<R, N, M, MODE_PLAIN>(a, max_smem_optin, stream);
+  } else {
+    return -1;
+  }
+}
+
+}  // namespace mpcb200
