@@ -17,7 +17,15 @@ from ._lib import MpcB200Error, check, ptr, stream_handle
 def pnqp(H, q, lower, upper, x_init=None, n_iter=20):
     if not H.is_cuda:
         raise MpcB200Error("mpc.pytorch_b200 runs on CUDA tensors only (no CPU fallback)")
+    if H.dim() != 3 or H.shape[1] != H.shape[2]:
+        raise MpcB200Error(f"H: expected [B,n,n], got {tuple(H.shape)}")
     B, n, _ = H.size()
+    for nm, t_ in (("q", q), ("lower", lower), ("upper", upper), ("x_init", x_init)):
+        if torch.is_tensor(t_):
+            if t_.device != H.device:
+                raise MpcB200Error(f"{nm}: expected a tensor on {H.device}, got {t_.device}")
+            if tuple(t_.shape) not in ((B, n), (n,), (1, n)):
+                raise MpcB200Error(f"{nm}: expected shape {(B, n)}, got {tuple(t_.shape)}")
     if n > 8:
         raise MpcB200Error(f"pnqp kernels are compiled for n <= 8 (got {n}); inside LQRStep the QP size is n_ctrl")
     dtype, dev = H.dtype, H.device

@@ -129,6 +129,7 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
   bool ok = aligned16(C) && aligned16(c) && aligned16(cur_x) && aligned16(cur_u) &&
             (F == nullptr || aligned16(F)) && (!d->has_f || aligned16(f)) &&
             (d->bounds_kind != 2 || (aligned16(u_lower) && aligned16(u_upper)));
+  ok = ok && (x_init == nullptr || aligned16(x_init));
   ok = ok && ((size_t)d->B * d->m * sz) % 16 == 0 && ((size_t)d->B * d->n * sz) % 16 == 0;
   a.bulk_ok = ok ? 1 : 0;
   if (const char* k = std::getenv("MPCB200_KERNEL")) a.impl = std::atoi(k);   // developer A/B knob: 1 generic, 2 pair

@@ -206,7 +206,10 @@ MPCB_DEV void pnqp_lane(const R (&H)[M][M], const R (&q)[M], const R (&lo)[M], c
     for (int a = 0; a < M; ++a) x[a] = -t[a];
   }
 #pragma unroll
-  for (int a = 0; a < M; ++a) x[a] = x[a] < lo[a] ? lo[a] : (x[a] > hi[a] ? hi[a] : x[a]);  // :23
+  for (int a = 0; a < M; ++a) {                // :23  util.eclamp: lower bound first, then upper
+    x[a] = x[a] < lo[a] ? lo[a] : x[a];
+    x[a] = x[a] > hi[a] ? hi[a] : x[a];
+  }
 
   for (int i = 0; i < max_iter; ++i) {
     R g[M];
@@ -257,7 +260,8 @@ MPCB_DEV void pnqp_lane(const R (&H)[M][M], const R (&q)[M], const R (&lo)[M], c
 #pragma unroll
       for (int a = 0; a < M; ++a) {
         const R v = x[a] + alpha * dx[a];
-        mx[a] = v < lo[a] ? lo[a] : (v > hi[a] ? hi[a] : v);
+        const R vl = v < lo[a] ? lo[a] : v;
+        mx[a] = vl > hi[a] ? hi[a] : vl;
       }
       R den = R(0);
 #pragma unroll
@@ -957,7 +961,8 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
             lo = l2 < lo ? lo : l2;
             hi = h2 > hi ? hi : h2;
           }
-          u[q] = u[q] < lo ? lo : (u[q] > hi ? hi : u[q]);
+          u[q] = u[q] < lo ? lo : u[q];                                   // util.eclamp order: lower, then upper
+          u[q] = u[q] > hi ? hi : u[q];
         }
         const R d = ubar.get(q) - u[q];
         dun2 += d * d;

@@ -82,6 +82,21 @@ MPCB_DEV R dot_span(const R (&a)[CNT], const R (&b)[CNT]) {
   return acc.x + acc.y;
 }
 
+// two dot products against the same vector, FMAs interleaved (two independent chains per pair slot)
+template <typename R, int CNT>
+MPCB_DEV void dot2_span(const R (&a0)[CNT], const R (&a1)[CNT], const R (&b)[CNT], R& r0, R& r1) {
+  static_assert(CNT % 2 == 0, "pairs");
+  P2<R> acc0 = mul2(P2<R>{a0[0], a0[1]}, P2<R>{b[0], b[1]});
+  P2<R> acc1 = mul2(P2<R>{a1[0], a1[1]}, P2<R>{b[0], b[1]});
+#pragma unroll
+  for (int k = 2; k < CNT; k += 2) {
+    acc0 = fma2(P2<R>{a0[k], a0[k + 1]}, P2<R>{b[k], b[k + 1]}, acc0);
+    acc1 = fma2(P2<R>{a1[k], a1[k + 1]}, P2<R>{b[k], b[k + 1]}, acc1);
+  }
+  r0 = acc0.x + acc0.y;
+  r1 = acc1.x + acc1.y;
+}
+
 template <typename R, int N, int M>
 struct Step2Cfg {
   static constexpr int P = N + M;
@@ -92,21 +107,15 @@ struct Step2Cfg {
   static constexpr int NW = MPCB2_NW;        // independent warps per CTA
   static constexpr int EA = 16 / (int)sizeof(R);
   static constexpr int SZ = (int)sizeof(R);
-  // shapes this mapping supports: even n, m; per-warp spans of every tensor 16-byte multiples
-  static constexpr bool OK = (N % 2 == 0) && (M % 2 == 0) && L <= 16 && (PPW * M * SZ) % 16 == 0 &&
-                             (PPW * N * SZ) % 16 == 0 && (PPW * P * SZ) % 16 == 0;
-  // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
+  // shapes this mapping supports: even n, m; per-warp spans of C and F 16-byte multiples (always true for even
+  // n, m) and per-problem vectors that the lanes read straight from global memory with vector loads
+  static constexpr bool OK = (N % 2 == 0) && (M % 2 == 0) && L <= 16 && N >= 2 && M >= 2;
+  // stage layout (elements): dense spans of the warp's PPW problems of C[t] and F[t]
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + PPW * P * P;
-  static constexpr int OFF_c = OFF_F + PPW * N * P;
-  static constexpr int OFF_x = OFF_c + PPW * P;
-  static constexpr int OFF_u = OFF_x + PPW * N;
-  static constexpr int OFF_f = OFF_u + PPW * M;
-  static constexpr int OFF_lo = OFF_f + PPW * N;
-  static constexpr int OFF_hi = OFF_lo + PPW * M;
-  static constexpr int OFF_END = OFF_hi + PPW * M;
+  static constexpr int OFF_END = OFF_F + PPW * N * P;
   static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
-  // per-problem scratch (elements); strides chosen so the PPW problems of a warp hit distinct 16-byte bank groups
+  // per-problem scratch (elements)
   static constexpr int NV = round_up(N, 4);             // row stride of V / K rows (16-byte aligned rows)
   static constexpr int VSTR = NV;
   static constexpr int SC_V = 0;                         // N x NV value matrix, row-major
@@ -117,11 +126,11 @@ struct Step2Cfg {
   static constexpr int SC_K = SC_R + round_up(L, 4);     // M x NV + M gain exchange when gains are not smem resident
   static constexpr int KT = M * NV + round_up(M, 4);     // elements per (problem, t) of the gain store
   static constexpr int SC_RAW = SC_K + KT;
-  // guaranteed alignment (elements) of per-problem spans inside a stage
+  // guaranteed alignment (elements) of per-problem vectors in global memory (bases are 16-byte aligned)
   static constexpr int A_N = align_elems<R>(N), A_M = align_elems<R>(M), A_P = align_elems<R>(P);
   static constexpr int pick_scr() {
-    // smallest stride >= SC_RAW, multiple of 4, with (stride % 32) in {4, 12, 20, 28}: consecutive problems
-    // then start 4 banks apart (mod 32) and broadcast 128-bit loads of up to 8 problems never collide
+    // smallest stride >= SC_RAW, multiple of 4, with stride % 8 == 4: consecutive problems then start an odd
+    // number of 16-byte bank groups apart and broadcast 128-bit loads of up to 8 problems never collide
     int s = round_up(SC_RAW, 4);
     while (s % 8 != 4) s += 4;
     return s;
@@ -136,38 +145,21 @@ struct Step2Cfg {
   static size_t smem_bytes(int T, bool k_in_smem) { return (size_t)NW * warp_smem_bytes(T, k_in_smem); }
 };
 
-
-// Synchronous tile copy for shapes / tails the bulk path cannot take (spans not 16-byte aligned): plain loads
-// by the whole warp, no prefetch.  Kept out of line: it is never on the hot path.
-template <typename R, int N, int M>
-__device__ __noinline__ void tile_copy_sync(const void* gC, const void* gF, const void* gc, const void* gx, const void* gu,
-                                            const void* gf, const void* glo, const void* ghi, int B, int T, R* st, int t,
-                                            bool needf, int b0, int cnt, int lane) {
-  using K = Step2Cfg<R, N, M>;
-  constexpr int P = K::P;
-  const size_t tb = (size_t)t * B + b0;
-  auto cp = [&](int off, const void* src, int per) {
-    const R* g = (const R*)src + tb * per;
-#pragma unroll 1
-    for (int i = lane; i < cnt * per; i += 32) st[off + i] = g[i];
-  };
-  cp(K::OFF_C, gC, P * P);
-  if (t < T - 1) cp(K::OFF_F, gF, N * P);
-  cp(K::OFF_c, gc, P);
-  cp(K::OFF_x, gx, N);
-  cp(K::OFF_u, gu, M);
-  if (needf) cp(K::OFF_f, gf, N);
-  if (glo != nullptr) {
-    cp(K::OFF_lo, glo, M);
-    cp(K::OFF_hi, ghi, M);
-  }
-}
-
 #ifdef MPCB2_TIMING
 #define TICK2(arr, i) { ck1 = clock64(); arr[i] += ck1 - ck0; ck0 = ck1; }
 #else
 #define TICK2(arr, i)
 #endif
+
+// per-(t, problem) vectors a lane reads straight from global memory, one or two steps ahead of their use
+template <typename R, int N, int M>
+struct SmallTile {
+  R tb[N + M];          // nominal point [x_bar; u_bar]
+  P2<R> cj;             // c[c0], c[c0+1]
+  P2<R> fj;             // f[xr0], f[xr0+1]     (rollout only)
+  R lo[M], hi[M];       // tensor bounds        (bounds_kind == 2 only)
+  unsigned zm;          // u_zero_I bits
+};
 
 template <typename R, int N, int M, int MODE>
 __global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32)
@@ -201,84 +193,80 @@ lqr_step2_kernel(const StepArgs a) {
   const int c0 = 2 * lq;                                    // first owned column (x then u columns)
   const int ua0 = isx ? 0 : c0 - N;                         // first owned control (u lanes)
   const int xr0 = isx ? c0 : 0;                             // a valid state row for every lane
+  const int bsafe = valid ? b : B - 1;
 
   // ------------------------------------------------------------------ tile streaming (this warp's own ring)
-  const bool tail_ok = (cnt == PPW) || (((cnt * M * SZ) % 16 == 0) && ((cnt * N * SZ) % 16 == 0) &&
-                                        ((cnt * P * SZ) % 16 == 0));
-  const bool bulk = a.bulk_ok && tail_ok;
-  // tile streaming: warp-uniform addresses, lane 0 issues one 1-D bulk copy per tensor
-  const size_t e0 = (size_t)b0;
-  const char* pC = (const char*)a.C + e0 * (P * P) * SZ;
-  const char* pF = (const char*)a.F + e0 * (N * P) * SZ;
-  const char* pc = (const char*)a.c + e0 * P * SZ;
-  const char* px = (const char*)a.cur_x + e0 * N * SZ;
-  const char* pu = (const char*)a.cur_u + e0 * M * SZ;
-  const char* pf = (const char*)a.f + e0 * N * SZ;
-  const char* plo = (const char*)a.u_lower + e0 * M * SZ;
-  const char* phi = (const char*)a.u_upper + e0 * M * SZ;
-  const uint32_t ucnt = (uint32_t)cnt;
-  const uint32_t by_base = ucnt * (P * P + P + N + M) * SZ + (a.bounds_kind == 2 ? 2u * ucnt * M * SZ : 0u);
-  const uint32_t by_F = ucnt * N * P * SZ, by_f = ucnt * N * SZ;
-
+  // Two 1-D bulk copies per tile (C[t] and F[t] spans of the warp's problems), issued by one lane right after
+  // the warp has finished reading the stage they overwrite.
+  const char* pC = (const char*)a.C + (size_t)b0 * (P * P) * SZ;
+  const char* pF = (const char*)a.F + (size_t)b0 * (N * P) * SZ;
+  const size_t strC = (size_t)B * (P * P) * SZ, strF = (size_t)B * (N * P) * SZ;
+  const uint32_t by_C = (uint32_t)cnt * (P * P) * SZ, by_F = (uint32_t)cnt * (N * P) * SZ;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
   __syncwarp();
-
-  int iss = 0;                                              // tiles issued so far (stage = iss % S)
-  auto issue = [&](int t, bool fwd) {
-    if (bulk) {
-      const int s = iss % S;
+  int iss_s = 0;                                            // stage of the next tile to issue
+  auto issue = [&](int t) {
+    if (lane == 0) {
+      unsigned char* dst = stage_base + (size_t)iss_s * K::STAGE_BYTES;
+      uint64_t* bar = &full[iss_s];
       const bool needF = t < T - 1;
-      const bool needf = fwd && needF && a.has_f;
-      if (lane == 0) {
-        unsigned char* dst = stage_base + (size_t)s * K::STAGE_BYTES;
-        uint64_t* bar = &full[s];
-        const size_t tB = (size_t)t * B;
-        mbar_arrive_expect_tx(bar, by_base + (needF ? by_F : 0u) + (needf ? by_f : 0u));
-        bulk_g2s(dst + K::OFF_C * SZ, pC + tB * (P * P) * SZ, ucnt * (P * P) * SZ, bar);
-        if (needF) bulk_g2s(dst + K::OFF_F * SZ, pF + tB * (N * P) * SZ, by_F, bar);
-        bulk_g2s(dst + K::OFF_c * SZ, pc + tB * P * SZ, ucnt * P * SZ, bar);
-        bulk_g2s(dst + K::OFF_x * SZ, px + tB * N * SZ, ucnt * N * SZ, bar);
-        bulk_g2s(dst + K::OFF_u * SZ, pu + tB * M * SZ, ucnt * M * SZ, bar);
-        if (needf) bulk_g2s(dst + K::OFF_f * SZ, pf + tB * N * SZ, by_f, bar);
-        if (a.bounds_kind == 2) {
-          bulk_g2s(dst + K::OFF_lo * SZ, plo + tB * M * SZ, ucnt * M * SZ, bar);
-          bulk_g2s(dst + K::OFF_hi * SZ, phi + tB * M * SZ, ucnt * M * SZ, bar);
-        }
-      }
+      mbar_arrive_expect_tx(bar, by_C + (needF ? by_F : 0u));
+      bulk_g2s(dst + K::OFF_C * SZ, pC + (size_t)t * strC, by_C, bar);
+      if (needF) bulk_g2s(dst + K::OFF_F * SZ, pF + (size_t)t * strF, by_F, bar);
     }
-    ++iss;
+    iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
   };
-  int con = 0;                                              // tiles consumed so far
-  // wait for tile `con` (bulk) or copy it synchronously (unaligned shapes / tails); returns the stage pointer
-  auto acquire = [&](int t, bool fwd) -> const R* {
-    const int s = con % S;
-    R* st = (R*)(stage_base + (size_t)s * K::STAGE_BYTES);
-    if (bulk) {
-      mbar_wait(&full[s], (uint32_t)((con / S) & 1));
-    } else {
-      tile_copy_sync<R, N, M>(a.C, a.F, a.c, a.cur_x, a.cur_u, a.f, a.bounds_kind == 2 ? a.u_lower : nullptr, a.u_upper, B, T,
-                              st, t, fwd && t < T - 1 && a.has_f, b0, cnt, lane);
-      __syncwarp();
-    }
-    ++con;
+  int con_s = 0;                                            // stage / phase parity of the next tile to consume
+  uint32_t con_ph = 0;
+  auto acquire = [&]() -> const R* {
+    const R* st = (const R*)(stage_base + (size_t)con_s * K::STAGE_BYTES);
+    mbar_wait(&full[con_s], con_ph);
+    if (++con_s == S) { con_s = 0; con_ph ^= 1u; }
     return st;
   };
-  // global tile sequence of the sweep + first rollout pass: g < T -> (T-1-g, backward), else (g-T, forward)
+  // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
   const int G = T + (a.do_rollout ? T : 0);
-  auto issue_g = [&](int g) {
-    if (g < T) issue(T - 1 - g, false);
-    else issue(g - T, true);
-  };
+  auto issue_g = [&](int g) { issue(g < T ? T - 1 - g : g - T); };
   for (int g = 0; g < S && g < G; ++g) issue_g(g);
+
+  // ------------------------------------------------------------------ small per-step vectors: global -> registers
+  const R* gc = (const R*)a.c;
+  const R* gcx = (const R*)a.cur_x;
+  const R* gcu = (const R*)a.cur_u;
+  const R* gf = (const R*)a.f;
+  const R* glo = (const R*)a.u_lower;
+  const R* ghi = (const R*)a.u_upper;
+  const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
+  using Small = SmallTile<R, N, M>;
+  auto fetch = [&](int t, bool fwd, Small& o) {
+    const size_t tb_ = (size_t)t * B + bsafe;
+    R tx[N], tu[M];
+    load_span<R, N, A_N>(gcx + tb_ * N, tx);
+    load_span<R, M, A_M>(gcu + tb_ * M, tu);
+#pragma unroll
+    for (int i = 0; i < N; ++i) o.tb[i] = tx[i];
+#pragma unroll
+    for (int q = 0; q < M; ++q) o.tb[N + q] = tu[q];
+    o.cj = ld_pair<R>(gc + tb_ * P + c0);
+    o.fj = {R(0), R(0)};
+    if (fwd && a.has_f && t < T - 1) o.fj = ld_pair<R>(gf + tb_ * N + xr0);
+    if (BOX && a.bounds_kind == 2) {
+      load_span<R, M, A_M>(glo + tb_ * M, o.lo);
+      load_span<R, M, A_M>(ghi + tb_ * M, o.hi);
+    }
+    o.zm = 0u;
+    if (has_mask) {
+#pragma unroll
+      for (int q = 0; q < M; ++q) o.zm |= (a.zero_mask[tb_ * M + q] ? 1u : 0u) << q;
+    }
+  };
 
   // per-problem element offsets inside a stage
   const int oC = K::OFF_C + pi * P * P, oF = K::OFF_F + pi * N * P;
-  const int oc = K::OFF_c + pi * P, of_ = K::OFF_f + pi * N, ox = K::OFF_x + pi * N, ou = K::OFF_u + pi * M;
-  const int olo = K::OFF_lo + pi * M, ohi = K::OFF_hi + pi * M;
   R* scr = scratch + (size_t)pi * K::SCRS;
   R* Vs = scr + K::SC_V;
   R* vs = scr + K::SC_v;
@@ -289,8 +277,6 @@ lqr_step2_kernel(const StepArgs a) {
   R* gKs = (R*)a.Ks;
   R* gks = (R*)a.ks;
   const R s_lo = (R)a.u_lo, s_hi = (R)a.u_hi, s_du = (R)a.delta_u, decay = (R)a.ls_decay;
-  const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
-  const int bsafe = valid ? b : B - 1;
 
   unsigned status = 0u;
   R oldcost_part = R(0);
@@ -303,30 +289,20 @@ lqr_step2_kernel(const StepArgs a) {
 #endif
 
   // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
+  Small sm_cur, sm_n1, sm_n2;                      // step t, t-1, t-2 (two steps of global-load latency hidden)
+  fetch(T - 1, false, sm_n1);
+  if (T > 1) fetch(T - 2, false, sm_n2);
   for (int t = T - 1; t >= 0; --t) {
 #ifdef MPCB2_TIMING
     ck0 = clock64();
 #endif
-    const R* st = acquire(t, false);
+    sm_cur = sm_n1;
+    sm_n1 = sm_n2;
+    if (t >= 2) fetch(t - 2, false, sm_n2);
+    const R* st = acquire();
     TICK2(tk, 0)
-    // zero-mask bytes of this (t, problem): tiny, read straight from global
-    unsigned zm = 0u;
-    if (has_mask) {
-#pragma unroll
-      for (int q = 0; q < M; ++q) zm |= (a.zero_mask[((size_t)t * B + bsafe) * M + q] ? 1u : 0u) << q;
-    }
-    // nominal point tau_bar replicated on every lane
-    R tb[P];
-    {
-      R tx[N], tu[M];
-      load_span<R, N, A_N>(st + ox, tx);
-      load_span<R, M, A_M>(st + ou, tu);
-#pragma unroll
-      for (int i = 0; i < N; ++i) tb[i] = tx[i];
-#pragma unroll
-      for (int q = 0; q < M; ++q) tb[N + q] = tu[q];
-    }
-    // owned column pair of C_t and F_t; rows c0, c0+1 of C_t for c_back = C tau_bar + c (lqr_step.py:289-295)
+    const R (&tb)[P] = sm_cur.tb;
+    // owned column pair of C_t; rows c0, c0+1 of C_t for c_back = C tau_bar + c (lqr_step.py:289-295)
     P2<R> Qp[P];                                   // (Q[i][c0], Q[i][c0+1])
 #pragma unroll
     for (int i = 0; i < P; ++i) Qp[i] = ld_pair<R>(st + oC + i * P + c0);
@@ -335,43 +311,54 @@ lqr_step2_kernel(const StepArgs a) {
       R Cr0[P], Cr1[P];
       load_span<R, P, EA>(st + oC + c0 * P, Cr0);          // c0 * P is a multiple of 4
       load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
-      const R ct0 = dot_span<R, P>(Cr0, tb), ct1 = dot_span<R, P>(Cr1, tb);
-      const P2<R> cj = ld_pair<R>(st + oc + c0);
-      const P2<R> tj = ld_pair<R>(st + (isx ? ox + c0 : ou + ua0));
-      if (writer_lane) oldcost_part += tj.x * (R(0.5) * ct0 + cj.x) + tj.y * (R(0.5) * ct1 + cj.y);   // util.get_cost (:169)
-      qp = {ct0 + cj.x, ct1 + cj.y};
+      R ct0, ct1;
+      dot2_span<R, P>(Cr0, Cr1, tb, ct0, ct1);
+      R tj0 = tb[0], tj1 = tb[1];                  // tau_bar[c0], tau_bar[c0+1] (c0 is lane dependent: select)
+#pragma unroll
+      for (int i = 2; i < P; i += 2)
+        if (c0 == i) { tj0 = tb[i]; tj1 = tb[i + 1]; }
+      if (writer_lane) oldcost_part += tj0 * (R(0.5) * ct0 + sm_cur.cj.x) + tj1 * (R(0.5) * ct1 + sm_cur.cj.y);   // util.get_cost (:169)
+      qp = {ct0 + sm_cur.cj.x, ct1 + sm_cur.cj.y};
     }
     TICK2(tk, 1)
     if (t < T - 1) {                               // Q = C + F'VF, q = c_back + F'v  (:66-70)
       P2<R> Fp[N];                                 // (F[k][c0], F[k][c0+1])
 #pragma unroll
       for (int k = 0; k < N; ++k) Fp[k] = ld_pair<R>(st + oF + k * P + c0);
-      P2<R> Wp[N];                                 // (W[i][c0], W[i][c0+1]),  W = V F
+      R Vr[N][N];                                  // the whole value matrix (broadcast 128-bit loads)
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        R Vr[N];
-        load_span<R, N, EA>(Vs + i * VSTR, Vr);
-        Wp[i] = {R(0), R(0)};
+      for (int i = 0; i < N; ++i) load_span<R, N, EA>(Vs + i * VSTR, Vr[i]);
+      R vv[N];
+      load_span<R, N, EA>(vs, vv);
+      P2<R> Wp[N];                                 // (W[i][c0], W[i][c0+1]),  W = V F : N independent FMA chains
 #pragma unroll
-        for (int k = 0; k < N; ++k) Wp[i] = fma2s(Fp[k], Vr[k], Wp[i]);
+      for (int i = 0; i < N; ++i) Wp[i] = mul2(Fp[0], P2<R>{Vr[i][0], Vr[i][0]});
+#pragma unroll
+      for (int k = 1; k < N; ++k) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) Wp[i] = fma2s(Fp[k], Vr[i][k], Wp[i]);
       }
-      // Q[:, pair] += F' W[:, pair]: rows of F come as 2-row chunks of the flat tile (16-byte aligned)
+      // Q[:, pair] += F' W[:, pair]: rows of F come as 2-row chunks of the flat tile; P independent chains
 #pragma unroll
       for (int k = 0; k < N; k += 2) {
         R Fr[2 * P];
         load_span<R, 2 * P, EA>(st + oF + k * P, Fr);     // k even: k * P is a multiple of 4
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-          Qp[i] = fma2s(Wp[k], Fr[i], Qp[i]);
-          Qp[i] = fma2s(Wp[k + 1], Fr[P + i], Qp[i]);
-        }
+        for (int i = 0; i < P; ++i) Qp[i] = fma2s(Wp[k], Fr[i], Qp[i]);
+#pragma unroll
+        for (int i = 0; i < P; ++i) Qp[i] = fma2s(Wp[k + 1], Fr[P + i], Qp[i]);
       }
-      R vv[N];
-      load_span<R, N, EA>(vs, vv);
 #pragma unroll
       for (int k = 0; k < N; ++k) qp = fma2s(Fp[k], vv[k], qp);
     }
     TICK2(tk, 2)
+    // the stage is consumed: refill it with tile g + S while the small solves run
+    __syncwarp();
+    {
+      const int g = (T - 1 - t) + S;
+      if (g < G) issue_g(g);
+    }
+    TICK2(tk, 7)
     // replicate Q_uu, q_u: control column a lives in lane base + NXL + a/2, component a%2
     R Quu[M][M], qu[M];
 #pragma unroll
@@ -390,8 +377,8 @@ lqr_step2_kernel(const StepArgs a) {
       R lb[M], ub[M];
 #pragma unroll
       for (int q = 0; q < M; ++q) {
-        const R lo_abs = a.bounds_kind == 2 ? st[olo + q] : s_lo;
-        const R hi_abs = a.bounds_kind == 2 ? st[ohi + q] : s_hi;
+        const R lo_abs = a.bounds_kind == 2 ? sm_cur.lo[q] : s_lo;
+        const R hi_abs = a.bounds_kind == 2 ? sm_cur.hi[q] : s_hi;
         const R ubq = tb[N + q];
         lb[q] = lo_abs - ubq;
         ub[q] = hi_abs - ubq;
@@ -420,7 +407,7 @@ lqr_step2_kernel(const StepArgs a) {
 #pragma unroll
       for (int q = 0; q < M; ++q) kprev[q] = kk[q];
     } else {                                       // unconstrained (:84-94) or u_zero_I masked (:100-127)
-      if constexpr (MODE == MODE_MASK) fm = FULLM & ~zm;
+      if constexpr (MODE == MODE_MASK) fm = FULLM & ~sm_cur.zm;
       R A[M][M], rhs[M], sol[M];
 #pragma unroll
       for (int p1 = 0; p1 < M; ++p1) {
@@ -505,26 +492,24 @@ lqr_step2_kernel(const StepArgs a) {
       R Kr[M][N];
 #pragma unroll
       for (int q = 0; q < M; ++q) load_span<R, N, EA>(Kt + q * NV, Kr[q]);
+      R qa[2 * M];                                 // Q_xu rows c0, c0+1 (x lanes; any valid rows otherwise)
+      load_span<R, 2 * M, (2 * M) % 4 == 0 ? 4 : 2>(Qx + xr0 * M, qa);
       P2<R> Vp[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        Vp[i] = Qp[i];
+      for (int i = 0; i < N; ++i) Vp[i] = Qp[i];
 #pragma unroll
-        for (int q = 0; q < M; ++q) {
-          Vp[i] = fma2s(Kp[q], Qf[i * M + q], Vp[i]);
-          Vp[i] = fma2s(Gp[q], Kr[q][i], Vp[i]);
-        }
+      for (int q = 0; q < M; ++q) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) Vp[i] = fma2s(Kp[q], Qf[i * M + q], Vp[i]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) Vp[i] = fma2s(Gp[q], Kr[q][i], Vp[i]);
       }
       P2<R> vp = qp;
-      {
-        R qa[2 * M];                               // Q_xu rows c0, c0+1 (x lanes; any valid rows otherwise)
-        load_span<R, 2 * M, (2 * M) % 4 == 0 ? 4 : 2>(Qx + xr0 * M, qa);
 #pragma unroll
-        for (int q = 0; q < M; ++q) {
-          vp.x += qa[q] * kk[q];
-          vp.y += qa[M + q] * kk[q];
-          vp = fma2s(Kp[q], gq[q], vp);
-        }
+      for (int q = 0; q < M; ++q) {
+        vp.x += qa[q] * kk[q];
+        vp.y += qa[M + q] * kk[q];
+        vp = fma2s(Kp[q], gq[q], vp);
       }
       if (writer_lane && isx) {
 #pragma unroll
@@ -534,11 +519,6 @@ lqr_step2_kernel(const StepArgs a) {
     }
     TICK2(tk, 6)
     __syncwarp();
-    {
-      const int g = (T - 1 - t) + S;
-      if (g < G) issue_g(g);
-    }
-    TICK2(tk, 7)
   }
 
   // nominal cost (sum of the lanes' partial sums, fixed order)
@@ -563,68 +543,65 @@ lqr_step2_kernel(const StepArgs a) {
   bool worse = false;
   for (int pass = 0;; ++pass) {
     if (pass > 0) {                                // line-search repeat: restart this warp's tile stream
-      for (int g = 0; g < S && g < T; ++g) issue(g, true);
+      for (int g = 0; g < S && g < T; ++g) issue(g);
     }
+    fetch(0, true, sm_n1);
+    if (T > 1) fetch(1, true, sm_n2);
     R xr[N];                                       // state replicated on every lane
-#pragma unroll
-    for (int i = 0; i < N; ++i) xr[i] = gx0[(size_t)bsafe * N + i];
-    P2<R> xown = {gx0[(size_t)bsafe * N + xr0], gx0[(size_t)bsafe * N + xr0 + 1]};
+    load_span<R, N, A_N>(gx0 + (size_t)bsafe * N, xr);
+    P2<R> xown = ld_pair<R>(gx0 + (size_t)bsafe * N + xr0);
     R cpart = R(0), dun2 = R(0);
     size_t orow = (size_t)bsafe;                   // t*B + b
     for (int t = 0; t < T; ++t, orow += (size_t)B) {
 #ifdef MPCB2_TIMING
       ck0 = clock64();
 #endif
-      const R* st = acquire(t, true);
+      sm_cur = sm_n1;
+      sm_n1 = sm_n2;
+      if (t + 2 < T) fetch(t + 2, true, sm_n2);
+      const R* st = acquire();
       TICK2(tf, 0)
-      unsigned zm = 0u;
-      if (has_mask) {
-#pragma unroll
-        for (int q = 0; q < M; ++q) zm |= (a.zero_mask[orow * M + q] ? 1u : 0u) << q;
-      }
-      R xb[N], ubar[M];
-      load_span<R, N, A_N>(st + ox, xb);
-      load_span<R, M, A_M>(st + ou, ubar);
+      const R (&tb)[P] = sm_cur.tb;
       R dxv[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) dxv[i] = xr[i] - xb[i];
+      for (int i = 0; i < N; ++i) dxv[i] = xr[i] - tb[i];
       R u[M];
       {
         const R* Kt = a.k_in_smem ? kst + (size_t)t * KT : nullptr;
         const R* Kg = gKs + orow * M * N;
         const R* kg = gks + orow * M;
+        R Krow[M][N], kq[M];
 #pragma unroll
         for (int q = 0; q < M; ++q) {
-          R Krow[N];
-          R kq;
           if (a.k_in_smem) {
-            load_span<R, N, EA>(Kt + q * NV, Krow);
-            kq = Kt[M * NV + q];
+            load_span<R, N, EA>(Kt + q * NV, Krow[q]);
+            kq[q] = Kt[M * NV + q];
           } else {
 #pragma unroll
-            for (int i = 0; i < N; ++i) Krow[i] = __ldcg(Kg + q * N + i);
-            kq = __ldcg(kg + q);
+            for (int i = 0; i < N; ++i) Krow[q][i] = __ldcg(Kg + q * N + i);
+            kq[q] = __ldcg(kg + q);
           }
-          u[q] = (dot_span<R, N>(Krow, dxv) + ubar[q]) + alpha * kq;          // (:192)
         }
+#pragma unroll
+        for (int q = 0; q < M; ++q) u[q] = (dot_span<R, N>(Krow[q], dxv) + tb[N + q]) + alpha * kq[q];   // (:192)
       }
 #pragma unroll
       for (int q = 0; q < M; ++q) {
         if constexpr (MODE != MODE_PLAIN) {
-          if (has_mask && ((zm >> q) & 1u)) u[q] = R(0);                     // (:197-198)
+          if (has_mask && ((sm_cur.zm >> q) & 1u)) u[q] = R(0);             // (:197-198)
         }
         if constexpr (BOX) {                                                // (:200-213)
-          R lo = a.bounds_kind == 2 ? st[olo + q] : s_lo;
-          R hi = a.bounds_kind == 2 ? st[ohi + q] : s_hi;
+          R lo = a.bounds_kind == 2 ? sm_cur.lo[q] : s_lo;
+          R hi = a.bounds_kind == 2 ? sm_cur.hi[q] : s_hi;
           if (a.has_delta) {
-            const R l2 = ubar[q] - s_du, h2 = ubar[q] + s_du;
+            const R l2 = tb[N + q] - s_du, h2 = tb[N + q] + s_du;
             lo = l2 < lo ? lo : l2;
             hi = h2 > hi ? hi : h2;
           }
           u[q] = u[q] < lo ? lo : u[q];                                       // util.eclamp: lower, then upper
           u[q] = u[q] > hi ? hi : u[q];
         }
-        const R d = ubar[q] - u[q];
+        const R d = tb[N + q] - u[q];
         dun2 += d * d;
       }
       TICK2(tf, 1)
@@ -635,50 +612,50 @@ lqr_step2_kernel(const StepArgs a) {
       for (int q = 0; q < M; ++q) tau[N + q] = u[q];
       // own pair of tau: x lanes carry it, u lanes pick their controls
       P2<R> tj = xown;
+      P2<R> ubj = {tb[N], tb[N + 1]};
       if (!isx) {
 #pragma unroll
         for (int q = 0; q < M; q += 2)
-          if (q == ua0) tj = {u[q], u[q + 1]};
+          if (q == ua0) {
+            tj = {u[q], u[q + 1]};
+            ubj = {tb[N + q], tb[N + q + 1]};
+          }
       }
       {
-        R Cr0[P], Cr1[P];
+        R Cr0[P], Cr1[P], Fr0[P], Fr1[P];
         load_span<R, P, EA>(st + oC + c0 * P, Cr0);
         load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
-        const P2<R> cj = ld_pair<R>(st + oc + c0);
-        if (writer_lane)
-          cpart += tj.x * (R(0.5) * dot_span<R, P>(Cr0, tau) + cj.x) + tj.y * (R(0.5) * dot_span<R, P>(Cr1, tau) + cj.y);   // (:232)
-      }
-      if (wr) {
-        if (isx) {
-          st_pair(gnx + orow * N + c0, tj);
-        } else {
-          st_pair(gnu + orow * M + ua0, tj);
-          if (pass == 0 && gdu1 != nullptr) {
-            const P2<R> ub2 = ld_pair<R>(st + ou + ua0);
-            st_pair(gdu1 + orow * M + ua0, P2<R>{ub2.x - tj.x, ub2.y - tj.y});
+        if (t < T - 1) {
+          load_span<R, P, EA>(st + oF + xr0 * P, Fr0);
+          load_span<R, P, 2>(st + oF + (xr0 + 1) * P, Fr1);
+        }
+        R ct0, ct1;
+        dot2_span<R, P>(Cr0, Cr1, tau, ct0, ct1);
+        if (writer_lane) cpart += tj.x * (R(0.5) * ct0 + sm_cur.cj.x) + tj.y * (R(0.5) * ct1 + sm_cur.cj.y);   // (:232)
+        if (wr) {
+          if (isx) {
+            st_pair(gnx + orow * N + c0, tj);
+          } else {
+            st_pair(gnu + orow * M + ua0, tj);
+            if (pass == 0 && gdu1 != nullptr) st_pair(gdu1 + orow * M + ua0, P2<R>{ubj.x - tj.x, ubj.y - tj.y});
           }
         }
-      }
-      TICK2(tf, 2)
-      if (t < T - 1) {                                                        // (:217-222)
-        R Fr0[P], Fr1[P];
-        load_span<R, P, EA>(st + oF + xr0 * P, Fr0);
-        load_span<R, P, 2>(st + oF + (xr0 + 1) * P, Fr1);
-        P2<R> xn = {dot_span<R, P>(Fr0, tau), dot_span<R, P>(Fr1, tau)};
-        if (a.has_f) {
-          const P2<R> fj = ld_pair<R>(st + of_ + xr0);
-          xn.x += fj.x;
-          xn.y += fj.y;
+        TICK2(tf, 2)
+        if (t < T - 1) {                                                      // (:217-222)
+          P2<R> xn;
+          dot2_span<R, P>(Fr0, Fr1, tau, xn.x, xn.y);
+          xn.x += sm_cur.fj.x;
+          xn.y += sm_cur.fj.y;
+          R* xsb = xs + (t & 1) * NV;
+          if (writer_lane && isx) st_pair(xsb + c0, xn);
+          xown = xn;
+          __syncwarp();
+          load_span<R, N, EA>(xsb, xr);
         }
-        R* xsb = xs + (t & 1) * NV;
-        if (writer_lane && isx) st_pair(xsb + c0, xn);
-        xown = xn;
-        __syncwarp();
-        load_span<R, N, EA>(xsb, xr);
       }
       TICK2(tf, 3)
       __syncwarp();
-      if (t + S < T) issue(t + S, true);
+      if (t + S < T) issue(t + S);
       TICK2(tf, 4)
     }
     if (writer_lane) red[lq] = cpart;
@@ -696,8 +673,8 @@ lqr_step2_kernel(const StepArgs a) {
   }
 #ifdef MPCB2_TIMING
   if (lane == 0 && (gw % 97) == 0)
-    printf("warp %d T=%d bwd/step: wait %lld pre %lld WQ %lld shfl %lld solve %lld Kexch %lld Vupd %lld issue %lld | fwd/step: wait %lld u %lld cost %lld dyn %lld issue %lld\n",
-           gw, T, tk[0] / T, tk[1] / T, tk[2] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T, tk[7] / T,
+    printf("warp %d T=%d bwd/step: wait %lld pre %lld WQ %lld issue %lld shfl %lld solve %lld Kexch %lld Vupd %lld | fwd/step: wait %lld u %lld cost %lld dyn %lld issue %lld\n",
+           gw, T, tk[0] / T, tk[1] / T, tk[2] / T, tk[7] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T,
            tf[0] / T, tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
 #endif
   if (worse) alpha /= decay;                                                  // (:252)
@@ -736,6 +713,7 @@ int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t str
 template <typename R, int N, int M>
 int launch_step2(const StepArgs& a, int max_smem_optin, cudaStream_t stream) {
   if constexpr (Step2Cfg<R, N, M>::OK) {
+    if (!a.bulk_ok) return -1;     // spans / bases not 16-byte aligned (odd batch sizes, sliced views): generic kernel
     if (a.bounds_kind != 0) return launch_step2_mode<R, N, M, MODE_BOX>(a, max_smem_optin, stream);
     if (a.has_mask) return launch_step2_mode<R, N, M, MODE_MASK>(a, max_smem_optin, stream);
     return launch_step2_mode<R, N, M, MODE_PLAIN>(a, max_smem_optin, stream);

@@ -32,6 +32,17 @@ def _dense(t, dtype=None):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _expect(name, t, shape, dev):
+    """The kernels read raw device pointers: a wrong shape or a tensor on another GPU would be an
+    out-of-bounds read, so fail here like the reference's indexing / eclamp size asserts would."""
+    if t is None:
+        return
+    if tuple(t.shape) != tuple(shape):
+        raise MpcB200Error(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.device != dev:
+        raise MpcB200Error(f"{name}: expected a tensor on {dev}, got {t.device}")
+
+
 # ----------------------------------------------------------------------------------------------
 # padding to a compiled (n,m) instance (compatibility path for shapes without an exact kernel)
 # ----------------------------------------------------------------------------------------------
@@ -135,7 +146,32 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     if dtype not in (torch.float32, torch.float64):
         raise MpcB200Error(f"unsupported dtype {dtype}")
     n, m = n_state, n_ctrl
+    if C.dim() != 4:
+        raise MpcB200Error(f"C: expected [T,B,n+m,n+m], got {tuple(C.shape)}")
     B = C.shape[1]
+    p = n + m
+    _expect("C", C, (T, B, p, p), dev)
+    _expect("c", c, (T, B, p), dev)
+    if not _is_empty(F):
+        if F.dim() != 4 or F.shape[0] not in (T - 1, T):
+            raise MpcB200Error(f"F: expected [T-1|T,B,n,n+m], got {tuple(F.shape)}")
+        _expect("F", F, (F.shape[0], B, n, p), dev)
+    elif T > 1:
+        raise MpcB200Error("F is required for T > 1")
+    if not _is_empty(f):
+        if f.dim() != 3 or f.shape[0] not in (T - 1, T):     # util.get_traj wants f.shape == F.shape[:3]
+            raise MpcB200Error(f"f: expected [T-1|T,B,n], got {tuple(f.shape)}")
+        _expect("f", f, (f.shape[0], B, n), dev)
+    _expect("x_init", x_init, (B, n), dev)
+    _expect("current_x", cur_x, (T, B, n), dev)
+    _expect("current_u", cur_u, (T, B, m), dev)
+    if (u_lower is None) != (u_upper is None):
+        raise MpcB200Error("u_lower and u_upper must be given together")
+    for nm, bnd in (("u_lower", u_lower), ("u_upper", u_upper)):
+        if torch.is_tensor(bnd):
+            _expect(nm, bnd, (T, B, m), dev)
+    if u_zero_I is not None:
+        _expect("u_zero_I", u_zero_I, (T, B, m), dev)
     N, M = _pick_instance(n, m)
     pad = _Pad(n, m, N, M, dev)
 
@@ -230,11 +266,21 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     return out
 
 
-def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_df):
+def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_df, f_T=None):
     """Run the gradient-assembly kernel; returns (dx_init, dC, dc, dF, df|None)."""
     dtype, dev = C.dtype, C.device
     n, m = n_state, n_ctrl
     B = C.shape[1]
+    p = n + m
+    _expect("C", C, (T, B, p, p), dev)
+    _expect("c", c, (T, B, p), dev)
+    if not _is_empty(F):
+        _expect("F", F, (F.shape[0], B, n, p), dev)
+        if F.shape[0] not in (T - 1, T):
+            raise MpcB200Error(f"F: expected T-1 or T time slices, got {F.shape[0]}")
+    for nm, t_, sh in (("new_x", new_x, (T, B, n)), ("new_u", new_u, (T, B, m)), ("dx", dx, (T, B, n)),
+                       ("du", du, (T, B, m)), ("dl_dx", dl_dx, (T, B, n))):
+        _expect(nm, t_, sh, dev)
     N, M = _pick_instance(n, m)
     pad = _Pad(n, m, N, M, dev)
     C_, c_ = _dense(C, dtype), _dense(c, dtype)
@@ -251,7 +297,11 @@ def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_
     dC = torch.empty(T, B, P, P, dtype=dtype, device=dev)
     dc = torch.empty(T, B, P, dtype=dtype, device=dev)
     dF = torch.empty(F_T, B, N, P, dtype=dtype, device=dev) if F_ is not None else None
-    df = torch.empty(T - 1, B, N, dtype=dtype, device=dev) if want_df else None
+    # df has f's leading dimension; the kernel writes slices < T-1, a T-th slice (full-length f) is zero
+    f_T = T - 1 if f_T is None else f_T
+    df = torch.empty(f_T, B, N, dtype=dtype, device=dev) if want_df else None
+    if want_df and f_T == T:
+        df[T - 1].zero_()
     dims = Dims(B=B, T=T, n=N, m=M, F_T=F_T if F_ is not None else T - 1, has_f=int(want_df),
                 bounds_kind=0, has_zero_mask=0, has_delta_u=0, max_ls_iter=1, pnqp_max_iter=1,
                 do_rollout=0)
@@ -279,6 +329,18 @@ def rollout_raw(n_state, n_ctrl, T, x_init, u, F, f=None):
         raise MpcB200Error("mpc.pytorch_b200 runs on CUDA tensors only (no CPU fallback)")
     n, m = n_state, n_ctrl
     B = x_init.shape[0]
+    _expect("x_init", x_init, (B, n), dev)
+    _expect("u", u, (T, B, m), dev)
+    if not _is_empty(F):
+        if F.dim() != 4 or F.shape[0] not in (T - 1, T):
+            raise MpcB200Error(f"F: expected [T-1|T,B,n,n+m], got {tuple(F.shape)}")
+        _expect("F", F, (F.shape[0], B, n, n + m), dev)
+    elif T > 1:
+        raise MpcB200Error("F is required for T > 1")
+    if not _is_empty(f):
+        if f.shape[0] not in (T - 1, T):
+            raise MpcB200Error(f"f: expected [T-1|T,B,n], got {tuple(f.shape)}")
+        _expect("f", f, (f.shape[0], B, n), dev)
     N, M = _pick_instance(n, m)
     pad = _Pad(n, m, N, M, dev)
     x0_, u_ = _dense(x_init, dtype), _dense(u, dtype)
@@ -309,7 +371,8 @@ def _bound_at(v, t):
 def _clamp_assign(x, lo, hi):
     lo = torch.as_tensor(lo, dtype=x.dtype, device=x.device).expand_as(x)
     hi = torch.as_tensor(hi, dtype=x.dtype, device=x.device).expand_as(x)
-    return torch.where(x > hi, hi, torch.where(x < lo, lo, x))
+    x = torch.where(x < lo, lo, x)          # util.eclamp order (reference mpc/util.py:64-68): lower, then upper
+    return torch.where(x > hi, hi, x)
 
 
 def _stage_cost(true_cost, tau, t):
@@ -482,7 +545,8 @@ def LQRStep(n_state,
                              do_rollout=True, want_stats=False)
             want_df = not _is_empty(f)
             dx_init, dC, dc, dF, df = lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u,
-                                                   o["new_x"], o["new_u"], dl_dx, want_df)
+                                                   o["new_x"], o["new_u"], dl_dx, want_df,
+                                                   f_T=f.shape[0] if want_df else None)
             if dF is None:
                 dF = torch.zeros_like(F)
             if df is None:                                       # reference :402 (empty tensor)

@@ -262,6 +262,26 @@ def main():
                                      max_linesearch_iter=dxr.max_linesearch_iter,
                                      grad_method=gm, eps=1e-2)(x0, rmpc.QuadCost(Q, pp), dxr)
         npz("cartpole_" + gm_name.lower() + "_f32", x_init=x0, Q=Q, p=pp, x=xs, u=us, costs=costs)
+    # ---------------------------------------------------------------- cartpole iLQR at BASELINE config 2 size
+    # B=128, T=25, bounds +-100, decay .5, 2 line-search iterations, eps 1e-2 (examples/Cartpole Control.ipynb
+    # cell 1 recipe).  float64 pins the algorithm to 1e-5; float32 is what the notebooks run.  lqr_iter is
+    # capped at 20 (f64) / 10 (f32): the comparison is per-iterate, more iterations only amplify fp32 noise.
+    if os.environ.get("GOLDEN_FULL", "1") == "1":
+        B, T = 128, 25
+        for tag, dtype, iters in (("f64", torch.float64, 20), ("f32", torch.float32, 10)):
+            x0 = initial_states(B, seed=0).to(dtype)
+            Q = torch.diag(q.data).to(dtype).unsqueeze(0).unsqueeze(0).repeat(T, B, 1, 1)
+            pp = p.data.to(dtype).unsqueeze(0).repeat(T, B, 1)
+            dxr_t = rcart.CartpoleDx(params=torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dtype))
+            with contextlib.redirect_stdout(io.StringIO()):
+                xs, us, costs = rmpc.MPC(5, 1, T, u_lower=dxr.lower, u_upper=dxr.upper, lqr_iter=iters, verbose=-1,
+                                         exit_unconverged=False, detach_unconverged=False,
+                                         linesearch_decay=dxr.linesearch_decay,
+                                         max_linesearch_iter=dxr.max_linesearch_iter,
+                                         grad_method=rmpc.GradMethods.AUTO_DIFF, eps=1e-2)(x0, rmpc.QuadCost(Q, pp), dxr_t)
+            assert xs.dtype == dtype
+            npz("cartpole_full_" + tag, x_init=x0, Q=Q[:1, :1], p=pp[:1, :1], x=xs, u=us, costs=costs,
+                lqr_iter=np.int64(iters))
     print("all golden fixtures written; oracle == reference on every case")
 
 
