@@ -23,7 +23,7 @@
 #include "lqr_step.cuh"
 
 #ifndef MPCB2_STAGES
-#define MPCB2_STAGES 3
+#define MPCB2_STAGES 4
 #endif
 #ifndef MPCB2_NW
 #define MPCB2_NW 1
@@ -196,8 +196,9 @@ lqr_step2_kernel(const StepArgs a) {
   const int bsafe = valid ? b : B - 1;
 
   // ------------------------------------------------------------------ tile streaming (this warp's own ring)
-  // Two 1-D bulk copies per tile (C[t] and F[t] spans of the warp's problems), issued by one lane right after
-  // the warp has finished reading the stage they overwrite.
+  // Two 1-D bulk copies per tile (C[t] and F[t] spans of the warp's problems).  The issue is branch free: one
+  // elected lane arrives with the byte count and starts the copies (predicated PTX), so the scheduler can
+  // overlap it with the scalar solve that follows the products.
   const char* pC = (const char*)a.C + (size_t)b0 * (P * P) * SZ;
   const char* pF = (const char*)a.F + (size_t)b0 * (N * P) * SZ;
   const size_t strC = (size_t)B * (P * P) * SZ, strF = (size_t)B * (N * P) * SZ;
@@ -208,23 +209,32 @@ lqr_step2_kernel(const StepArgs a) {
     mbar_fence_init();
   }
   __syncwarp();
+  const uint32_t stage0 = smem_u32(stage_base), bar0 = smem_u32(full);
   int iss_s = 0;                                            // stage of the next tile to issue
   auto issue = [&](int t) {
-    if (lane == 0) {
-      unsigned char* dst = stage_base + (size_t)iss_s * K::STAGE_BYTES;
-      uint64_t* bar = &full[iss_s];
-      const bool needF = t < T - 1;
-      mbar_arrive_expect_tx(bar, by_C + (needF ? by_F : 0u));
-      bulk_g2s(dst + K::OFF_C * SZ, pC + (size_t)t * strC, by_C, bar);
-      if (needF) bulk_g2s(dst + K::OFF_F * SZ, pF + (size_t)t * strF, by_F, bar);
-    }
+    const uint32_t dst = stage0 + (uint32_t)iss_s * K::STAGE_BYTES;
+    const uint32_t bar = bar0 + (uint32_t)iss_s * 8u;
+    const int needF = t < T - 1 ? 1 : 0;
+    asm volatile(
+        "{\n\t.reg .pred P, Q;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "setp.ne.and.b32 Q, %5, 0, P;\n\t"
+        "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%0];\n\t"
+        "@Q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%6], [%7], %8, [%0];\n\t"
+        "}" ::"r"(bar), "r"(by_C + (needF ? by_F : 0u)), "r"(dst + (uint32_t)K::OFF_C * SZ),
+        "l"(pC + (size_t)t * strC), "r"(by_C), "r"(needF), "r"(dst + (uint32_t)K::OFF_F * SZ),
+        "l"(pF + (size_t)t * strF), "r"(by_F)
+        : "memory");
     iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
   };
   int con_s = 0;                                            // stage / phase parity of the next tile to consume
   uint32_t con_ph = 0;
-  auto acquire = [&]() -> const R* {
+  // split acquire: probe early (the probe's latency overlaps the math that follows), block only if needed
+  auto probe = [&]() -> uint32_t { return mbar_try_wait(&full[con_s], con_ph) ? 1u : 0u; };
+  auto acquire = [&](uint32_t ok) -> const R* {
     const R* st = (const R*)(stage_base + (size_t)con_s * K::STAGE_BYTES);
-    mbar_wait(&full[con_s], con_ph);
+    if (!ok) mbar_wait(&full[con_s], con_ph);
     if (++con_s == S) { con_s = 0; con_ph ^= 1u; }
     return st;
   };
@@ -289,42 +299,54 @@ lqr_step2_kernel(const StepArgs a) {
 #endif
 
   // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
-  Small sm_cur, sm_n1, sm_n2;                      // step t, t-1, t-2 (two steps of global-load latency hidden)
-  fetch(T - 1, false, sm_n1);
-  if (T > 1) fetch(T - 2, false, sm_n2);
+  // Software pipelined by hand: everything of step t-1 that does not depend on the value matrix (tile probe,
+  // its column pairs of C and F, c_back = C tau_bar + c, the nominal cost) is issued inside step t, where it
+  // fills the latency of the scalar solve and of the shared-memory round trips.
+  P2<R> Qp[P];                                     // (Q[i][c0], Q[i][c0+1]); starts as the column pair of C_t
+  P2<R> qp;                                        // (q[c0], q[c0+1]);       starts as c_back
+  P2<R> Fp[N];                                     // (F[k][c0], F[k][c0+1])
+  R ubar[M], blo[M], bhi[M];                       // u_bar_t and tensor bounds of the step being solved
+  unsigned zmk = 0u;
+  Small sA, sB;                                    // small vectors of steps t-1 and t-2
+  // the V-independent part of step tt, from tile `stt` and small vectors `sm`
+  auto pre = [&](int tt, const R* stt, const Small& sm) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) Qp[i] = ld_pair<R>(stt + oC + i * P + c0);
+    R Cr0[P], Cr1[P];
+    load_span<R, P, EA>(stt + oC + c0 * P, Cr0);            // c0 * P is a multiple of 4
+    load_span<R, P, 2>(stt + oC + (c0 + 1) * P, Cr1);
+    R ct0, ct1;
+    dot2_span<R, P>(Cr0, Cr1, sm.tb, ct0, ct1);              // rows c0, c0+1 of C tau_bar (lqr_step.py:289-295)
+    R tj0 = sm.tb[0], tj1 = sm.tb[1];              // tau_bar[c0], tau_bar[c0+1] (c0 is lane dependent: select)
+#pragma unroll
+    for (int i = 2; i < P; i += 2)
+      if (c0 == i) { tj0 = sm.tb[i]; tj1 = sm.tb[i + 1]; }
+    if (writer_lane) oldcost_part += tj0 * (R(0.5) * ct0 + sm.cj.x) + tj1 * (R(0.5) * ct1 + sm.cj.y);   // util.get_cost (:169)
+    qp = {ct0 + sm.cj.x, ct1 + sm.cj.y};
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+      ubar[q] = sm.tb[N + q];
+      if (BOX && a.bounds_kind == 2) { blo[q] = sm.lo[q]; bhi[q] = sm.hi[q]; }
+    }
+    zmk = sm.zm;
+    (void)tt;
+  };
+  const R* st;
+  {
+    Small s0;
+    fetch(T - 1, false, s0);
+    if (T > 1) fetch(T - 2, false, sA);
+    if (T > 2) fetch(T - 3, false, sB);
+    st = acquire(0u);
+    pre(T - 1, st, s0);
+  }
   for (int t = T - 1; t >= 0; --t) {
 #ifdef MPCB2_TIMING
     ck0 = clock64();
 #endif
-    sm_cur = sm_n1;
-    sm_n1 = sm_n2;
-    if (t >= 2) fetch(t - 2, false, sm_n2);
-    const R* st = acquire();
-    TICK2(tk, 0)
-    const R (&tb)[P] = sm_cur.tb;
-    // owned column pair of C_t; rows c0, c0+1 of C_t for c_back = C tau_bar + c (lqr_step.py:289-295)
-    P2<R> Qp[P];                                   // (Q[i][c0], Q[i][c0+1])
-#pragma unroll
-    for (int i = 0; i < P; ++i) Qp[i] = ld_pair<R>(st + oC + i * P + c0);
-    P2<R> qp;
-    {
-      R Cr0[P], Cr1[P];
-      load_span<R, P, EA>(st + oC + c0 * P, Cr0);          // c0 * P is a multiple of 4
-      load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
-      R ct0, ct1;
-      dot2_span<R, P>(Cr0, Cr1, tb, ct0, ct1);
-      R tj0 = tb[0], tj1 = tb[1];                  // tau_bar[c0], tau_bar[c0+1] (c0 is lane dependent: select)
-#pragma unroll
-      for (int i = 2; i < P; i += 2)
-        if (c0 == i) { tj0 = tb[i]; tj1 = tb[i + 1]; }
-      if (writer_lane) oldcost_part += tj0 * (R(0.5) * ct0 + sm_cur.cj.x) + tj1 * (R(0.5) * ct1 + sm_cur.cj.y);   // util.get_cost (:169)
-      qp = {ct0 + sm_cur.cj.x, ct1 + sm_cur.cj.y};
-    }
-    TICK2(tk, 1)
+    uint32_t ok_next = 0u;
+    if (t > 0) ok_next = probe();                  // tile t-1: checked after the products
     if (t < T - 1) {                               // Q = C + F'VF, q = c_back + F'v  (:66-70)
-      P2<R> Fp[N];                                 // (F[k][c0], F[k][c0+1])
-#pragma unroll
-      for (int k = 0; k < N; ++k) Fp[k] = ld_pair<R>(st + oF + k * P + c0);
       R Vr[N][N];                                  // the whole value matrix (broadcast 128-bit loads)
 #pragma unroll
       for (int i = 0; i < N; ++i) load_span<R, N, EA>(Vs + i * VSTR, Vr[i]);
@@ -352,11 +374,17 @@ lqr_step2_kernel(const StepArgs a) {
       for (int k = 0; k < N; ++k) qp = fma2s(Fp[k], vv[k], qp);
     }
     TICK2(tk, 2)
-    // the stage is consumed: refill it with tile g + S while the small solves run
+    // tile t is consumed (its C pair / rows were read by pre(t)): refill the stage with tile g + S
     __syncwarp();
     {
       const int g = (T - 1 - t) + S;
       if (g < G) issue_g(g);
+    }
+    const R* st_next = st;
+    if (t > 0) {                                   // F column pair of step t-1: lands while the solve runs
+      st_next = acquire(ok_next);
+#pragma unroll
+      for (int k = 0; k < N; ++k) Fp[k] = ld_pair<R>(st_next + oF + k * P + c0);
     }
     TICK2(tk, 7)
     // replicate Q_uu, q_u: control column a lives in lane base + NXL + a/2, component a%2
@@ -377,11 +405,10 @@ lqr_step2_kernel(const StepArgs a) {
       R lb[M], ub[M];
 #pragma unroll
       for (int q = 0; q < M; ++q) {
-        const R lo_abs = a.bounds_kind == 2 ? sm_cur.lo[q] : s_lo;
-        const R hi_abs = a.bounds_kind == 2 ? sm_cur.hi[q] : s_hi;
-        const R ubq = tb[N + q];
-        lb[q] = lo_abs - ubq;
-        ub[q] = hi_abs - ubq;
+        const R lo_abs = a.bounds_kind == 2 ? blo[q] : s_lo;
+        const R hi_abs = a.bounds_kind == 2 ? bhi[q] : s_hi;
+        lb[q] = lo_abs - ubar[q];
+        ub[q] = hi_abs - ubar[q];
         if (a.has_delta) {
           if (lb[q] < -s_du) lb[q] = -s_du;
           if (ub[q] > s_du) ub[q] = s_du;
@@ -407,7 +434,7 @@ lqr_step2_kernel(const StepArgs a) {
 #pragma unroll
       for (int q = 0; q < M; ++q) kprev[q] = kk[q];
     } else {                                       // unconstrained (:84-94) or u_zero_I masked (:100-127)
-      if constexpr (MODE == MODE_MASK) fm = FULLM & ~sm_cur.zm;
+      if constexpr (MODE == MODE_MASK) fm = FULLM & ~zmk;
       R A[M][M], rhs[M], sol[M];
 #pragma unroll
       for (int p1 = 0; p1 < M; ++p1) {
@@ -440,34 +467,39 @@ lqr_step2_kernel(const StepArgs a) {
 #pragma unroll
       for (int q = 0; q < M; ++q) Kp[q] = {-s0[q], -s1[q]};
     }
-    if (writer_lane) {
-      if (isx) {
+    // publish: x lanes their K pair (rows of the gain store), u lanes their Q_xu pair as rows [i][a] -
+    // one predicated store sequence for both kinds of lanes (no divergent branches)
+    {
+      R* sbase = isx ? Kt + c0 : Qx + ua0;
+      const int sstr = isx ? NV : M;
 #pragma unroll
-        for (int q = 0; q < M; ++q) st_pair(Kt + q * NV + c0, Kp[q]);
-        if (lq == 0) {
+      for (int i = 0; i < (N > M ? N : M); ++i) {
+        const bool on = writer_lane && (isx ? i < M : i < N);
+        const P2<R> v = (isx && i < M) ? Kp[i < M ? i : 0] : Qp[i < N ? i : 0];
+        if (on) st_pair(sbase + i * sstr, v);
+      }
+      if (writer_lane && lq == 0) {
 #pragma unroll
-          for (int q = 0; q < M; ++q) Kt[M * NV + q] = kk[q];
-        }
-      } else {                                     // u lane: publish Q_xu[:, pair] as rows [i][a]
-#pragma unroll
-        for (int i = 0; i < N; ++i) st_pair(Qx + i * M + ua0, Qp[i]);
+        for (int q = 0; q < M; ++q) Kt[M * NV + q] = kk[q];
       }
     }
-    if (wr) {
-      const size_t tbo = (size_t)t * B + b;
-      if (gKs != nullptr && isx) {
+    if (gKs != nullptr || a.free_mask != nullptr || (BOX && a.qp_iters != nullptr)) {   // optional outputs
+      if (wr) {
+        const size_t tbo = (size_t)t * B + b;
+        if (gKs != nullptr && isx) {
 #pragma unroll
-        for (int q = 0; q < M; ++q) st_pair(gKs + (tbo * M + q) * N + c0, Kp[q]);
-        if (lq == 0) {
+          for (int q = 0; q < M; ++q) st_pair(gKs + (tbo * M + q) * N + c0, Kp[q]);
+          if (lq == 0) {
 #pragma unroll
-          for (int q = 0; q < M; ++q) gks[tbo * M + q] = kk[q];
+            for (int q = 0; q < M; ++q) gks[tbo * M + q] = kk[q];
+          }
         }
-      }
-      if (lq == 0) {
-        if (BOX && a.qp_iters != nullptr) a.qp_iters[tbo] = it;
-        if (a.free_mask != nullptr) {
+        if (lq == 0) {
+          if (BOX && a.qp_iters != nullptr) a.qp_iters[tbo] = it;
+          if (a.free_mask != nullptr) {
 #pragma unroll
-          for (int q = 0; q < M; ++q) a.free_mask[tbo * M + q] = (fm >> q) & 1u;
+            for (int q = 0; q < M; ++q) a.free_mask[tbo * M + q] = (fm >> q) & 1u;
+          }
         }
       }
     }
@@ -518,7 +550,15 @@ lqr_step2_kernel(const StepArgs a) {
       }
     }
     TICK2(tk, 6)
+    // V-independent part of step t-1, in the shadow of the V round trip through shared memory
+    if (t > 0) {
+      pre(t - 1, st_next, sA);
+      sA = sB;
+      if (t >= 3) fetch(t - 3, false, sB);
+      st = st_next;
+    }
     __syncwarp();
+    TICK2(tk, 1)
   }
 
   // nominal cost (sum of the lanes' partial sums, fixed order)
@@ -535,6 +575,9 @@ lqr_step2_kernel(const StepArgs a) {
   }
 
   // ======================= rollout + line search (lqr_step.py:164-261) =======================
+  // Per step the dependent chain is x -> u = K dx + .. -> clamp -> x' = F tau + f -> exchange.  The operands
+  // of step t+1 (gain rows, rows of C and F) are loaded into the registers of step t as soon as those are
+  // dead, so they are in flight while the chain of step t runs.
   const R* gx0 = (const R*)a.x_init;
   R* gnx = (R*)a.new_x;
   R* gnu = (R*)a.new_u;
@@ -545,54 +588,61 @@ lqr_step2_kernel(const StepArgs a) {
     if (pass > 0) {                                // line-search repeat: restart this warp's tile stream
       for (int g = 0; g < S && g < T; ++g) issue(g);
     }
-    fetch(0, true, sm_n1);
-    if (T > 1) fetch(1, true, sm_n2);
+    Small sm0;                                     // steps t, t+1, t+2
+    fetch(0, true, sm0);
+    if (T > 1) fetch(1, true, sA);
+    if (T > 2) fetch(2, true, sB);
     R xr[N];                                       // state replicated on every lane
     load_span<R, N, A_N>(gx0 + (size_t)bsafe * N, xr);
     P2<R> xown = ld_pair<R>(gx0 + (size_t)bsafe * N + xr0);
+    R Krow[M][N], kq[M], Cr0[P], Cr1[P], Fr0[P], Fr1[P];
+    auto load_gain = [&](int tt) {
+      const R* Kt = kst + (size_t)tt * KT;
+      const size_t row = (size_t)tt * B + bsafe;
+#pragma unroll
+      for (int q = 0; q < M; ++q) {
+        if (a.k_in_smem) {
+          load_span<R, N, EA>(Kt + q * NV, Krow[q]);
+          kq[q] = Kt[M * NV + q];
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) Krow[q][i] = __ldcg(gKs + (row * M + q) * N + i);
+          kq[q] = __ldcg(gks + row * M + q);
+        }
+      }
+    };
+    st = acquire(0u);
+    load_gain(0);
+    load_span<R, P, EA>(st + oC + c0 * P, Cr0);
+    load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
+    if (T > 1) {
+      load_span<R, P, EA>(st + oF + xr0 * P, Fr0);
+      load_span<R, P, 2>(st + oF + (xr0 + 1) * P, Fr1);
+    }
     R cpart = R(0), dun2 = R(0);
     size_t orow = (size_t)bsafe;                   // t*B + b
     for (int t = 0; t < T; ++t, orow += (size_t)B) {
 #ifdef MPCB2_TIMING
       ck0 = clock64();
 #endif
-      sm_cur = sm_n1;
-      sm_n1 = sm_n2;
-      if (t + 2 < T) fetch(t + 2, true, sm_n2);
-      const R* st = acquire();
-      TICK2(tf, 0)
-      const R (&tb)[P] = sm_cur.tb;
+      uint32_t ok_next = 0u;
+      if (t + 1 < T) ok_next = probe();            // tile t+1
+      const R (&tb)[P] = sm0.tb;
       R dxv[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) dxv[i] = xr[i] - tb[i];
       R u[M];
-      {
-        const R* Kt = a.k_in_smem ? kst + (size_t)t * KT : nullptr;
-        const R* Kg = gKs + orow * M * N;
-        const R* kg = gks + orow * M;
-        R Krow[M][N], kq[M];
 #pragma unroll
-        for (int q = 0; q < M; ++q) {
-          if (a.k_in_smem) {
-            load_span<R, N, EA>(Kt + q * NV, Krow[q]);
-            kq[q] = Kt[M * NV + q];
-          } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) Krow[q][i] = __ldcg(Kg + q * N + i);
-            kq[q] = __ldcg(kg + q);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < M; ++q) u[q] = (dot_span<R, N>(Krow[q], dxv) + tb[N + q]) + alpha * kq[q];   // (:192)
-      }
+      for (int q = 0; q < M; ++q) u[q] = (dot_span<R, N>(Krow[q], dxv) + tb[N + q]) + alpha * kq[q];   // (:192)
+      if (t + 1 < T) load_gain(t + 1);             // gain registers are dead: fetch the next step's rows
 #pragma unroll
       for (int q = 0; q < M; ++q) {
         if constexpr (MODE != MODE_PLAIN) {
-          if (has_mask && ((sm_cur.zm >> q) & 1u)) u[q] = R(0);             // (:197-198)
+          if (has_mask && ((sm0.zm >> q) & 1u)) u[q] = R(0);                // (:197-198)
         }
         if constexpr (BOX) {                                                // (:200-213)
-          R lo = a.bounds_kind == 2 ? sm_cur.lo[q] : s_lo;
-          R hi = a.bounds_kind == 2 ? sm_cur.hi[q] : s_hi;
+          R lo = a.bounds_kind == 2 ? sm0.lo[q] : s_lo;
+          R hi = a.bounds_kind == 2 ? sm0.hi[q] : s_hi;
           if (a.has_delta) {
             const R l2 = tb[N + q] - s_du, h2 = tb[N + q] + s_du;
             lo = l2 < lo ? lo : l2;
@@ -621,41 +671,46 @@ lqr_step2_kernel(const StepArgs a) {
             ubj = {tb[N + q], tb[N + q + 1]};
           }
       }
-      {
-        R Cr0[P], Cr1[P], Fr0[P], Fr1[P];
-        load_span<R, P, EA>(st + oC + c0 * P, Cr0);
-        load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
-        if (t < T - 1) {
-          load_span<R, P, EA>(st + oF + xr0 * P, Fr0);
-          load_span<R, P, 2>(st + oF + (xr0 + 1) * P, Fr1);
-        }
-        R ct0, ct1;
-        dot2_span<R, P>(Cr0, Cr1, tau, ct0, ct1);
-        if (writer_lane) cpart += tj.x * (R(0.5) * ct0 + sm_cur.cj.x) + tj.y * (R(0.5) * ct1 + sm_cur.cj.y);   // (:232)
-        if (wr) {
-          if (isx) {
-            st_pair(gnx + orow * N + c0, tj);
-          } else {
-            st_pair(gnu + orow * M + ua0, tj);
-            if (pass == 0 && gdu1 != nullptr) st_pair(gdu1 + orow * M + ua0, P2<R>{ubj.x - tj.x, ubj.y - tj.y});
-          }
-        }
-        TICK2(tf, 2)
-        if (t < T - 1) {                                                      // (:217-222)
-          P2<R> xn;
-          dot2_span<R, P>(Fr0, Fr1, tau, xn.x, xn.y);
-          xn.x += sm_cur.fj.x;
-          xn.y += sm_cur.fj.y;
-          R* xsb = xs + (t & 1) * NV;
-          if (writer_lane && isx) st_pair(xsb + c0, xn);
-          xown = xn;
-          __syncwarp();
-          load_span<R, N, EA>(xsb, xr);
+      P2<R> xn = {R(0), R(0)};
+      if (t < T - 1) {                                                        // (:217-222) - the chain first
+        dot2_span<R, P>(Fr0, Fr1, tau, xn.x, xn.y);
+        xn.x += sm0.fj.x;
+        xn.y += sm0.fj.y;
+        if (writer_lane && isx) st_pair(xs + (t & 1) * NV + c0, xn);
+      }
+      R ct0, ct1;
+      dot2_span<R, P>(Cr0, Cr1, tau, ct0, ct1);
+      if (writer_lane) cpart += tj.x * (R(0.5) * ct0 + sm0.cj.x) + tj.y * (R(0.5) * ct1 + sm0.cj.y);   // (:232)
+      if (wr) {
+        if (isx) {
+          st_pair(gnx + orow * N + c0, tj);
+        } else {
+          st_pair(gnu + orow * M + ua0, tj);
+          if (pass == 0 && gdu1 != nullptr) st_pair(gdu1 + orow * M + ua0, P2<R>{ubj.x - tj.x, ubj.y - tj.y});
         }
       }
-      TICK2(tf, 3)
+      TICK2(tf, 2)
+      // rows of C and F of step t+1 into the (now dead) registers of step t
+      const R* st_next = st;
+      if (t + 1 < T) {
+        st_next = acquire(ok_next);
+        load_span<R, P, EA>(st_next + oC + c0 * P, Cr0);
+        load_span<R, P, 2>(st_next + oC + (c0 + 1) * P, Cr1);
+        if (t + 2 < T) {
+          load_span<R, P, EA>(st_next + oF + xr0 * P, Fr0);
+          load_span<R, P, 2>(st_next + oF + (xr0 + 1) * P, Fr1);
+        }
+      }
+      xown = xn;
       __syncwarp();
+      if (t < T - 1) load_span<R, N, EA>(xs + (t & 1) * NV, xr);
+      TICK2(tf, 3)
+      sm0 = sA;
+      sA = sB;
+      if (t + 3 < T) fetch(t + 3, true, sB);
+      // tile t is consumed (its rows were loaded one step ago): refill its stage
       if (t + S < T) issue(t + S);
+      st = st_next;
       TICK2(tf, 4)
     }
     if (writer_lane) red[lq] = cpart;
@@ -673,9 +728,9 @@ lqr_step2_kernel(const StepArgs a) {
   }
 #ifdef MPCB2_TIMING
   if (lane == 0 && (gw % 97) == 0)
-    printf("warp %d T=%d bwd/step: wait %lld pre %lld WQ %lld issue %lld shfl %lld solve %lld Kexch %lld Vupd %lld | fwd/step: wait %lld u %lld cost %lld dyn %lld issue %lld\n",
-           gw, T, tk[0] / T, tk[1] / T, tk[2] / T, tk[7] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T,
-           tf[0] / T, tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
+    printf("warp %d T=%d bwd/step: WQ %lld issue+Fp %lld shfl %lld solve %lld Kexch %lld Vupd %lld pre %lld | fwd/step: u %lld dyn+cost %lld next+xchg %lld issue %lld\n",
+           gw, T, tk[2] / T, tk[7] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T, tk[1] / T,
+           tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
 #endif
   if (worse) alpha /= decay;                                                  // (:252)
   if (wr && lq == 0) {
