@@ -133,9 +133,6 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
   ok = ok && ((size_t)d->B * d->m * sz) % 16 == 0 && ((size_t)d->B * d->n * sz) % 16 == 0;
   a.bulk_ok = ok ? 1 : 0;
   if (const char* k = std::getenv("MPCB200_KERNEL")) a.impl = std::atoi(k);   // developer A/B knob: 1 generic, 2 pair
-#ifdef MPCB_DEBUG_KNOBS   // developer builds only: MPCB200_DEBUG=1 (no data movement) / 2 (no math) give WRONG results
-  if (const char* dbg = std::getenv("MPCB200_DEBUG")) a.debug = std::atoi(dbg);
-#endif
   rc = (sizeof(R) == 4 ? e->step32 : e->step64)(a, smem, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(1);
   return rc;

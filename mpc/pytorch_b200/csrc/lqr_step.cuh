@@ -24,9 +24,10 @@
 //  * line search: per-problem alpha; a CTA repeats the rollout while any of its problems is
 //    worse and iterations remain - per problem this is exactly the reference's batch loop.
 //  * MODE (template): PLAIN / BOX (pnqp) / MASK (u_zero_I adjoint solve) - no mode branches at run time.
-// Compile-time knobs kept from measured experiments (all off / default): MPCB_STAGES, MPCB_CPL,
-// MPCB_VREG, MPCB_PADTILES, MPCB_MMA16, MPCB_TIMING (per-phase clock64 report); with -DMPCB_DEBUG_KNOBS the
-// env var MPCB200_DEBUG (1: no data movement, 2: no math) isolates bottlenecks.  See DESIGN.md section 7.
+// This is the GENERIC kernel (any n, m <= 32 lanes, unaligned spans): shapes with even n, m and 16-byte
+// aligned tensors run the column-pair kernel in lqr_step2.cuh.  The round-1 experiments that lived here as
+// compile-time knobs (two columns per lane, V in registers, padded tiles, mma.sync products, phase timers)
+// are described with their measurements in DESIGN.md section 7; their code was removed.
 #pragma once
 #include <cstdio>
 #include "common.cuh"
@@ -50,7 +51,6 @@ struct StepArgs {
   void *Ks, *ks;
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
-  int debug;      // developer experiments (env MPCB200_DEBUG): 1 = no data movement, 2 = no math
   int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh)
 };
 
@@ -59,16 +59,7 @@ struct StepCfg {
   static constexpr int P = N + M;
   static constexpr int EA = 16 / (int)sizeof(R);
   static_assert(P <= 32, "one problem must fit a warp");
-  // columns per lane: 2 when the problem is wide enough (halves the shared-memory operand traffic
-  // per problem and doubles the independent FMA streams per lane), else 1.  Slot 0 of every lane
-  // must be a state column (LP <= N).
-  // Measured on B200 (config 3): CPL=2 is SLOWER (49 vs 41 us): with the whole batch resident in one
-  // wave the kernel time is (steps) x (per-step latency of a warp), and two columns per lane lengthen
-  // that chain.  Kept as a compile-time knob.
-#ifndef MPCB_CPL
-#define MPCB_CPL 1
-#endif
-  static constexpr int CPL = (MPCB_CPL == 2 && P >= 8 && (P + 1) / 2 <= N) ? 2 : 1;
+  static constexpr int CPL = 1;                     // columns per lane
   static constexpr int LP = (P + CPL - 1) / CPL;   // lanes per problem
   static constexpr int PPW = 32 / LP;               // problems per warp
   // consumer warps per CTA: the smallest count whose per-time-step spans stay 16-byte aligned for every
@@ -86,36 +77,7 @@ struct StepCfg {
   static constexpr int THREADS = (NW + 1) * 32;
   static constexpr int S = MPCB_STAGES;   // ring stages
   static constexpr int VS = round_up(N, 4);
-  // Per-problem strides of the C and F tiles inside a stage.  The PPW problems of a warp read the same
-  // tile offsets at the same time, so their bank windows must not overlap: pad the stride (in 16-byte
-  // steps) to the value with the fewest overlapping banks; each problem's tile is then its own bulk copy.
-  static constexpr int bank_overlap(int stride) {
-    int words = (int)sizeof(R) / 4, hit = 0;
-    for (int a = 0; a < PPW; ++a)
-      for (int b2 = a + 1; b2 < PPW; ++b2) {
-        int d = ((b2 - a) * stride * words) % 32;
-        if (d > 16) d = 32 - d;
-        int ov = P * words - d;
-        hit += ov > 0 ? ov : 0;
-      }
-    return hit;
-  }
-  static constexpr int pick_stride(int dense) {
-    if ((dense * (int)sizeof(R)) % 16 != 0 || PPW == 1) return dense;   // per-problem bulk copies need 16B multiples
-    int best = dense, best_hit = bank_overlap(dense);
-    for (int pad = EA; pad <= 32; pad += EA) {
-      int h = bank_overlap(dense + pad);
-      if (h < best_hit) { best = dense + pad; best_hit = h; }
-    }
-    return best;
-  }
-  // Measured on B200, config 3: the PPW small bulk copies per tensor cost more than the removed bank
-  // conflicts save (51 us vs 38 us).  Off by default; kept as a knob.
-#ifndef MPCB_PADTILES
-#define MPCB_PADTILES 0
-#endif
-  static constexpr int CS = MPCB_PADTILES ? pick_stride(P * P) : P * P;
-  static constexpr int FS = MPCB_PADTILES ? pick_stride(N * P) : N * P;
+  static constexpr int CS = P * P, FS = N * P;     // per-problem strides of the C and F tiles inside a stage
   // stage tile offsets (elements); every sub-tile starts 16-byte aligned (span_ok / padded strides)
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + W * CS;
@@ -128,35 +90,14 @@ struct StepCfg {
   static constexpr int OFF_END = OFF_hi + W * M;
   static constexpr int STAGE_BYTES = round_up(OFF_END * (int)sizeof(R) + round_up(W * M, 16), 128);
   // per-problem scratch (elements)
-  static constexpr int PS = round_up(P, 4);      // padded row stride of the W exchange buffer
-  // VREG: the value matrix stays in registers and the rows of F are register resident during the
-  // two products (needs N*P registers per lane; small problems only).  Measured on B200, config 3:
-  // 25 % fewer shared-memory loads but one more exchange per step -> 38.9 us vs 38.0 us (B=4096) and
-  // 250 us vs 230 us (B=32768).  Off by default; kept as a knob.
-#ifndef MPCB_VREG
-#define MPCB_VREG 0
-#endif
-  static constexpr bool VREG = MPCB_VREG && CPL == 1 && N * P * (int)sizeof(R) <= 400;
-  static constexpr int SC_V = 0;                 // VREG: N x PS  W = V F exchange; else N x VS value matrix
-  static constexpr int SC_v = SC_V + N * (VREG ? PS : VS);     // VS      value vector
+  static constexpr int SC_V = 0;                 // N x VS value matrix
+  static constexpr int SC_v = SC_V + N * VS;     // VS      value vector
   static constexpr int SC_K = SC_v + VS;         // M x VS (+ M) K_t,k_t exchange when gains are not smem resident
   static constexpr int KT = M * VS + round_up(M, 4);  // elements per (problem, t) of the gain store
   static constexpr int SC_Q = SC_K + KT;         // M x VS  Q_xu exchange (row a = Q[:n, n+a])
   static constexpr int SC_X = SC_Q + M * VS;     // 2 x VS  rollout state exchange
   static constexpr int SC_R = SC_X + 2 * VS;     // cost reduction
-  // n=16, m=4, fp32: optional tensor-core path for the two dense products of the sweep (mma.sync m16n8k8
-  // TF32 in three passes, fp32 accumulate; Q comes back through a P x 24 shared buffer).  Parity-green, 3.3x
-  // fewer shared-memory wavefronts - but measured SLOWER inside this kernel (757 vs 677 us at B=4096, T=50):
-  // with the gain store in shared memory only 2 CTAs (8 warps) fit an SM, so the step is latency bound and
-  // the mma chain is no shorter than the FFMA2 one (and with the gains in global memory the kernel is register limited).  The standalone probe (tools/mma_probe.cu, all warps
-  // resident) needs 2.5 us per step for the same products: the win needs an occupancy fix first (gains in
-  // global/L2 or a smaller ring).  Off by default.
-#ifndef MPCB_MMA16
-#define MPCB_MMA16 0
-#endif
-  static constexpr bool MMA16 = MPCB_MMA16 && N == 16 && M == 4 && sizeof(R) == 4 && CPL == 1;
-  static constexpr int SC_QT = SC_R + round_up(P, 4);
-  static constexpr int SC_RAW = SC_QT + (MMA16 ? P * 24 : 0);
+  static constexpr int SC_RAW = SC_R + round_up(P, 4);
   static constexpr int SCR = (SC_RAW % 32 == 0 || SC_RAW % 32 == 16) ? SC_RAW + 4 : SC_RAW;
   // KREDUCE: when the gains live in the caller's Ks/ks buffer (long horizons / large n), lane i reads only
   // column i of K_t and the products are butterfly-reduced over the n state lanes (needs one problem per
@@ -321,9 +262,7 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
       unsigned char* mk = (unsigned char*)(st + K::OFF_END);
       for (int i = lane; i < cnt * M; i += 32) mk[i] = a.zero_mask[tb * M + i];
     }
-    if (a.debug & 1) {
-      if (lane == 0) mbar_arrive(&full[s]);
-    } else if (bulk) {
+    if (bulk) {
       __syncwarp();
       if (lane == 0) {
         uint32_t bytes = (uint32_t)cnt * (P * P + P + N + M) * SZ;
@@ -388,98 +327,6 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
 
 
 // ---------------------------------------------------------------------------------------------
-// tensor-core helpers (mma.sync.m16n8k8, TF32 operands, fp32 accumulate; 3xTF32 = hi*hi + hi*lo + lo*hi)
-// ---------------------------------------------------------------------------------------------
-MPCB_DEV void tf32_split(float x, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-MPCB_DEV void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-MPCB_DEV void mma_3xtf32(float (&d)[4], const unsigned (&ah)[4], const unsigned (&al)[4],
-                         const unsigned (&bh)[2], const unsigned (&bl)[2]) {
-  mma_tf32(d, al, bh);
-  mma_tf32(d, ah, bl);
-  mma_tf32(d, ah, bh);
-}
-
-// Q = C + F'(V F) for ONE problem per warp, n=16, p=20 (measured in tools/mma_probe.cu).  F, C: dense
-// row-major tiles in shared memory; Vt[c*VS + i] = V[i][c]; the result is written to QT[a*24 + b].
-MPCB_DEV void wq_products_mma16(const float* Fp, const float* Cp, const float* Vt, int VS, float* QT, int lane) {
-  constexpr int NN = 16, PP = 20;
-  const int g = lane >> 2, t = lane & 3;
-  unsigned Ah[2][2][4], Al[2][2][4];          // A fragments of F': rows a = mt*16+g(+8), cols k = ks*8+t(+4)
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int a = mt * 16 + g + (r & 1) * 8, k = ks * 8 + t + (r >> 1) * 4;
-        tf32_split(a < PP ? Fp[k * PP + a] : 0.f, Ah[mt][ks][r], Al[mt][ks][r]);
-      }
-  float Wt[2][2][4];                          // W' = F'V in accumulator layout
-  {
-    unsigned Vh[2][2][2], Vl[2][2][2];        // B fragments of V: k = ks*8+t(+4), n = nt*8+g
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-          tf32_split(Vt[(nt * 8 + g) * VS + ks * 8 + t + r * 4], Vh[ks][nt][r], Vl[ks][nt][r]);
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) Wt[mt][nt][r] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) mma_3xtf32(Wt[mt][nt], Ah[mt][ks], Al[mt][ks], Vh[ks][nt], Vl[ks][nt]);
-      }
-  }
-  unsigned Wh[2][3][2], Wl[2][3][2];          // accumulator layout -> B fragments of W (quad shuffles)
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-    for (int nt = 0; nt < 3; ++nt) {
-      const int mt = nt >> 1, hi8 = (nt & 1) * 2;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int src = (lane & ~3) | ((t + r * 4) >> 1);
-        const float xe = __shfl_sync(0xffffffffu, Wt[mt][ks][hi8 + 0], src);
-        const float xo = __shfl_sync(0xffffffffu, Wt[mt][ks][hi8 + 1], src);
-        tf32_split((t & 1) ? xo : xe, Wh[ks][nt][r], Wl[ks][nt][r]);
-      }
-    }
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 3; ++nt) {
-      float acc[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int a = mt * 16 + g + (r >> 1) * 8, b = nt * 8 + 2 * t + (r & 1);
-        acc[r] = (a < PP && b < PP) ? Cp[a * PP + b] : 0.f;
-      }
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) mma_3xtf32(acc, Ah[mt][ks], Al[mt][ks], Wh[ks][nt], Wl[ks][nt]);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int a = mt * 16 + g + h * 8;
-        if (a < PP) *reinterpret_cast<float2*>(QT + a * 24 + nt * 8 + 2 * t) = make_float2(acc[2 * h], acc[2 * h + 1]);
-      }
-    }
-  (void)NN;
-}
-MPCB_DEV void wq_products_mma16(const double*, const double*, const double*, int, double*, int) {}   // never used
-
-// ---------------------------------------------------------------------------------------------
 // consumer warps.  MODE (compile time): 0 plain (no bounds, no mask), 1 box (pnqp; optional
 // u_zero_I), 2 mask (u_zero_I only - the adjoint solve).
 // ---------------------------------------------------------------------------------------------
@@ -542,32 +389,13 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
   uint32_t ph = 0;
   unsigned status = 0u;
   R oldcost_part = R(0);
-#ifdef MPCB_TIMING
-  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tf[6] = {0, 0, 0, 0, 0, 0};
-  long long c0, c1;
-#define TICK(arr, i) { c1 = clock64(); arr[i] += c1 - c0; c0 = c1; }
-#else
-#define TICK(arr, i)
-#endif
   R kprev[M];
 #pragma unroll
   for (int q = 0; q < M; ++q) kprev[q] = R(0);
-  Vec<R, N> Vreg;                         // VREG: column j of the value matrix
-  Vreg.zero();
 
   // ======================= backward Riccati sweep (lqr_step.py:61-158) =======================
   for (int t = T - 1; t >= 0; --t) {
-#ifdef MPCB_TIMING
-    c0 = clock64();
-#endif
     mbar_wait(&full[stg], ph);
-    TICK(tk, 0)
-    if (a.debug & 2) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stg]);
-      if (++stg == K::S) { stg = 0; ph ^= 1u; }
-      continue;
-    }
     const R* st = (const R*)(stage_base + (size_t)stg * K::STAGE_BYTES);
     const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
 
@@ -598,44 +426,11 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
       if (wsl[sl]) oldcost_part += tbj * (R(0.5) * Ct + cj);   // util.get_cost of the nominal trajectory (:169)
       qj[sl] = Ct + cj;
     }
-
-    TICK(tk, 1)
     if (t < T - 1) {                            // Q = C + F'VF, q = c_back + F'v  (:66-70)
       Vec<R, N> Fcol[CPL], Wc[CPL];
 #pragma unroll
       for (int sl = 0; sl < CPL; ++sl) Fcol[sl].gather(st + oF + cc[sl], P);
-      if constexpr (K::MMA16) {
-        // tensor-core path: operands are fetched once per warp as fragments instead of once per lane
-        R* QT = scr + K::SC_QT;
-        wq_products_mma16(st + oF, st + oC, Vs, VS, QT, lane);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < P; ++i) Qc[0].set(i, QT[i * 24 + cc[0]]);   // column j of Q (C already included)
-      } else if constexpr (K::VREG) {
-        // V stays in registers: lane i holds V[:, i] (used as row i - V is symmetric up to round-off and
-        // the transposed use is stable).  Rows of F are loaded ONCE into
-        // registers and feed both products: W[i, :] = sum_k V[i,k] F[k, :] on the state lanes, then,
-        // after a transpose of W through shared memory, Q[:, j] += sum_k F[k, :]' W[k, j] on every lane.
-        Vec<R, P> Frow[N];
-        static_for<0, N>([&](auto kc) {
-          constexpr int k = decltype(kc)::value;
-          constexpr int AK = k % 2 == 0 ? A_2P : align_elems<R>(P);
-          Frow[k].template load<(AK < A_NP ? AK : A_NP)>(st + oF + k * P);
-        });
-        Vec<R, P> Wrow;
-        Wrow.zero();
-#pragma unroll
-        for (int k = 0; k < N; ++k) Wrow.axpy(Frow[k], Vreg.get(k));
-        if (wsl[0] && isx[0]) {
-          R* dst = Vs + cc[0] * K::PS;
-#pragma unroll
-          for (int i = 0; i < P; ++i) dst[i] = Wrow.get(i);
-        }
-        __syncwarp();
-        Wc[0].gather(Vs + cc[0], K::PS);          // column j of W
-#pragma unroll
-        for (int k = 0; k < N; ++k) Qc[0].axpy(Frow[k], Wc[0].get(k));
-      } else {
+      {
 #pragma unroll
         for (int sl = 0; sl < CPL; ++sl) Wc[sl].zero();
 #pragma unroll
@@ -659,8 +454,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
       for (int sl = 0; sl < CPL; ++sl) qj[sl] += Fcol[sl].dot(vv);
     }
-
-    TICK(tk, 2)
     // replicate Q_uu, q_u on every lane of the problem (column n+b2 lives in lane (n+b2)%LP, slot (n+b2)/LP)
     R Quu[M][M], qu[M];
 #pragma unroll
@@ -672,8 +465,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
       for (int p1 = 0; p1 < M; ++p1) Quu[p1][p2] = shfl(Qc[(N + p2) / LP].get(N + p1), src);
       qu[p2] = shfl(qj[(N + p2) / LP], src);
     }
-
-    TICK(tk, 3)
     R kk[M];
     unsigned fm = FULLM;
     int it = 0;
@@ -733,7 +524,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
       for (int q = 0; q < M; ++q) kk[q] = -sol[q];
     }
-    TICK(tk, 4)
     // K[:, c] = -Hff^{-1} Qux_f[:, c] for the owned columns (rows of clamped / masked controls are zero)
     R Kc[CPL][M];
     R* Kt = a.k_in_smem ? kst + (size_t)t * KT : kst;
@@ -784,7 +574,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
       }
     }
     __syncwarp();
-    TICK(tk, 5)
 
     // V = Qxx + Qxu K + K'Qux + K'Quu K ; v = qx + Qxu k + K'qu + K'Quu k   (:155-158)
     Vec<R, N> Vn[CPL];
@@ -821,22 +610,13 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
 #pragma unroll
     for (int sl = 0; sl < CPL; ++sl) {
       if (wsl[sl] && isx[sl]) {
-        if constexpr (!K::VREG) {
-          Vn[sl].template store<EA>(Vs + cc[sl] * VS);      // column c of V, stored as row c (vector stores)
-        }
+        Vn[sl].template store<EA>(Vs + cc[sl] * VS);        // column c of V, stored as row c (vector stores)
         vs[cc[sl]] = vn[sl];
       }
     }
-    if constexpr (K::VREG) {              // V[:, j] stays in this lane's registers (control lanes: zero)
-#pragma unroll
-      for (int k2 = 0; k2 < Vec<R, N>::NP; ++k2)
-        Vreg.p[k2] = isx[0] ? Vn[0].p[k2] : P2<R>{R(0), R(0)};
-    }
-    TICK(tk, 6)
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stg]);
     if (++stg == K::S) { stg = 0; ph ^= 1u; }
-    TICK(tk, 7)
   }
 
   // nominal cost  (sum of the lanes' partial sums, fixed order)
@@ -886,17 +666,7 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
     }
     size_t orow = (size_t)b;                     // t*B + b
     for (int t = 0; t < T; ++t, orow += (size_t)B) {
-#ifdef MPCB_TIMING
-      c0 = clock64();
-#endif
       mbar_wait(&full[stg], ph);
-      TICK(tf, 0)
-      if (a.debug & 2) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stg]);
-        if (++stg == K::S) { stg = 0; ph ^= 1u; }
-          continue;
-      }
       const R* st = (const R*)(stage_base + (size_t)stg * K::STAGE_BYTES);
       const unsigned char* mk = (const unsigned char*)(st + K::OFF_END) + pw * M;
 
@@ -967,7 +737,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
         const R d = ubar.get(q) - u[q];
         dun2 += d * d;
       }
-      TICK(tf, 1)
       Vec<R, P> tau;
 #pragma unroll
       for (int i = 0; i < N; ++i) tau.set(i, xr.get(i));
@@ -1004,7 +773,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
           if (a.has_f) xn[sl] += st[of_ + fr[sl]];
         }
       }
-      TICK(tf, 2)
       if (t < T - 1) {
         R* xsb = xs + (t & 1) * VS;
 #pragma unroll
@@ -1016,11 +784,9 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
         xr.template load<EA>(xsb);
         if constexpr (N & 1) xr.p[Vec<R, N>::NP - 1].y = R(0);
       }
-      TICK(tf, 3)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stg]);
       if (++stg == K::S) { stg = 0; ph ^= 1u; }
-      TICK(tf, 4)
     }
     if (writer_lane) red[j] = cpart;
     __syncwarp();
@@ -1038,12 +804,6 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
     const int cont = votes[pass & 31];
     if (!cont || !more) break;
   }
-#ifdef MPCB_TIMING
-  if (lane == 0 && (blockIdx.x % 97) == 0 && warp == 0)
-    printf("cta %d T=%d bwd/step: wait %lld pre %lld WQ %lld shfl %lld solve %lld Kexch %lld Vupd %lld rel %lld | fwd/step: wait %lld u %lld rows %lld xchg %lld rel %lld\n",
-           blockIdx.x, T, tk[0] / T, tk[1] / T, tk[2] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T, tk[7] / T,
-           tf[0] / T, tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
-#endif
   if (worse) alpha /= decay;                                      // (:252)
   if (wr && j == 0) {
     ((R*)a.costs)[b] = cost;
@@ -1078,16 +838,6 @@ lqr_step_kernel(const StepArgs a) {
     mbar_fence_init();
   }
   if (tid < 32) votes[tid] = 0;
-  if (a.debug & 1) {   // experiment: no data movement -> deterministic (identity-like) tiles
-    R* stf = reinterpret_cast<R*>(stage_base);
-    for (int i = tid; i < K::S * K::STAGE_BYTES / (int)sizeof(R); i += K::THREADS) stf[i] = R(0);
-    __syncthreads();
-    for (int s = 0; s < K::S; ++s)
-      for (int i = tid; i < K::W * K::P; i += K::THREADS) {
-        R* Ct = reinterpret_cast<R*>(stage_base + (size_t)s * K::STAGE_BYTES) + K::OFF_C;
-        Ct[(i / K::P) * K::CS + (i % K::P) * (K::P + 1)] = R(1);   // C = I
-      }
-  }
   __syncthreads();
   if (warp == K::NW) {
     step_producer<R, N, M>(a, stage_base, full, empty, votes, b0, cnt, lane);

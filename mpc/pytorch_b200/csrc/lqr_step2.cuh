@@ -109,11 +109,18 @@ struct Step2Cfg {
   static constexpr int SZ = (int)sizeof(R);
   // shapes this mapping supports: even n, m; per-warp spans of C and F 16-byte multiples (always true for even
   // n, m) and per-problem vectors that the lanes read straight from global memory with vector loads
-  static constexpr bool OK = (N % 2 == 0) && (M % 2 == 0) && L <= 16 && N >= 2 && M >= 2;
-  // stage layout (elements): dense spans of the warp's PPW problems of C[t] and F[t]
+  static constexpr bool OK = (N % 2 == 0) && (M % 2 == 0) && L <= 16 && N >= 2 && M >= 2 && (PPW * M * SZ) % 16 == 0 &&
+                             (PPW * N * SZ) % 16 == 0 && (PPW * P * SZ) % 16 == 0;
+  // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + PPW * P * P;
-  static constexpr int OFF_END = OFF_F + PPW * N * P;
+  static constexpr int OFF_c = OFF_F + PPW * N * P;
+  static constexpr int OFF_x = OFF_c + PPW * P;
+  static constexpr int OFF_u = OFF_x + PPW * N;
+  static constexpr int OFF_f = OFF_u + PPW * M;
+  static constexpr int OFF_lo = OFF_f + PPW * N;
+  static constexpr int OFF_hi = OFF_lo + PPW * M;
+  static constexpr int OFF_END = OFF_hi + PPW * M;
   static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
   // per-problem scratch (elements)
   static constexpr int NV = round_up(N, 4);             // row stride of V / K rows (16-byte aligned rows)
@@ -151,17 +158,7 @@ struct Step2Cfg {
 #define TICK2(arr, i)
 #endif
 
-// per-(t, problem) vectors a lane reads straight from global memory, one or two steps ahead of their use
-template <typename R, int N, int M>
-struct SmallTile {
-  R tb[N + M];          // nominal point [x_bar; u_bar]
-  P2<R> cj;             // c[c0], c[c0+1]
-  P2<R> fj;             // f[xr0], f[xr0+1]     (rollout only)
-  R lo[M], hi[M];       // tensor bounds        (bounds_kind == 2 only)
-  unsigned zm;          // u_zero_I bits
-};
-
-template <typename R, int N, int M, int MODE>
+template <typename R, int N, int M, int MODE, bool KSM>
 __global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32)
 lqr_step2_kernel(const StepArgs a) {
   using K = Step2Cfg<R, N, M>;
@@ -176,7 +173,7 @@ lqr_step2_kernel(const StepArgs a) {
   const int b0 = gw * PPW;
   if (b0 >= B) return;                                      // warps are independent: no CTA-wide barrier below
   const int cnt = min(PPW, B - b0);
-  unsigned char* wbase = smem_raw + (size_t)warp * K::warp_smem_bytes(T, a.k_in_smem != 0);
+  unsigned char* wbase = smem_raw + (size_t)warp * K::warp_smem_bytes(T, KSM);
   uint64_t* full = reinterpret_cast<uint64_t*>(wbase);
   unsigned char* stage_base = wbase + K::HDR_BYTES;
   R* scratch = reinterpret_cast<R*>(stage_base + (size_t)S * K::STAGE_BYTES);
@@ -196,13 +193,25 @@ lqr_step2_kernel(const StepArgs a) {
   const int bsafe = valid ? b : B - 1;
 
   // ------------------------------------------------------------------ tile streaming (this warp's own ring)
-  // Two 1-D bulk copies per tile (C[t] and F[t] spans of the warp's problems).  The issue is branch free: one
-  // elected lane arrives with the byte count and starts the copies (predicated PTX), so the scheduler can
-  // overlap it with the scalar solve that follows the products.
-  const char* pC = (const char*)a.C + (size_t)b0 * (P * P) * SZ;
-  const char* pF = (const char*)a.F + (size_t)b0 * (N * P) * SZ;
-  const size_t strC = (size_t)B * (P * P) * SZ, strF = (size_t)B * (N * P) * SZ;
-  const uint32_t by_C = (uint32_t)cnt * (P * P) * SZ, by_F = (uint32_t)cnt * (N * P) * SZ;
+  // One tile = the warp's spans of C[t], F[t], c[t], x_bar[t], u_bar[t] (+ f[t] in the rollout, + tensor
+  // bounds): up to eight 1-D bulk copies onto ONE mbarrier.  The issue is branch free - one elected lane arrives
+  // with the byte count and starts the copies (predicated PTX; UBLKCP executes once per warp) - so the scheduler
+  // overlaps it with the scalar solve that follows the products.  Nothing on the data path goes through the
+  // load/store scoreboards (global loads that are prefetched across loop iterations end up sharing a
+  // scoreboard with the mbarrier probe and expose the full DRAM latency every step - measured).
+  const size_t eb = (size_t)b0 * SZ;
+  const char* pC = (const char*)a.C + eb * (P * P);
+  const char* pF = (const char*)a.F + eb * (N * P);
+  const char* pc = (const char*)a.c + eb * P;
+  const char* px = (const char*)a.cur_x + eb * N;
+  const char* pu = (const char*)a.cur_u + eb * M;
+  const char* pf = (const char*)a.f + eb * N;
+  const char* plo = (const char*)a.u_lower + eb * M;
+  const char* phi = (const char*)a.u_upper + eb * M;
+  const size_t strB = (size_t)B * SZ;                       // bytes per time step and per element of a problem
+  const uint32_t ucnt = (uint32_t)cnt * SZ;                 // bytes per element-of-a-problem over the warp's problems
+  const int has_tb = (BOX && a.bounds_kind == 2) ? 1 : 0;
+  const uint32_t by_base = ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0));
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -211,20 +220,43 @@ lqr_step2_kernel(const StepArgs a) {
   __syncwarp();
   const uint32_t stage0 = smem_u32(stage_base), bar0 = smem_u32(full);
   int iss_s = 0;                                            // stage of the next tile to issue
-  auto issue = [&](int t) {
+  auto issue = [&](int t, bool fwd) {
     const uint32_t dst = stage0 + (uint32_t)iss_s * K::STAGE_BYTES;
     const uint32_t bar = bar0 + (uint32_t)iss_s * 8u;
     const int needF = t < T - 1 ? 1 : 0;
+    const int needf = (fwd && needF && a.has_f) ? 1 : 0;
+    const size_t tB = (size_t)t * strB;
     asm volatile(
-        "{\n\t.reg .pred P, Q;\n\t"
+        "{\n\t.reg .pred P, PF, Pf, PB;\n\t.reg .b32 d, n;\n\t"
         "elect.sync _|P, 0xffffffff;\n\t"
-        "setp.ne.and.b32 Q, %5, 0, P;\n\t"
+        "setp.ne.and.b32 PF, %12, 0, P;\n\t"
+        "setp.ne.and.b32 Pf, %13, 0, P;\n\t"
+        "setp.ne.and.b32 PB, %14, 0, P;\n\t"
         "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
-        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%0];\n\t"
-        "@Q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%6], [%7], %8, [%0];\n\t"
-        "}" ::"r"(bar), "r"(by_C + (needF ? by_F : 0u)), "r"(dst + (uint32_t)K::OFF_C * SZ),
-        "l"(pC + (size_t)t * strC), "r"(by_C), "r"(needF), "r"(dst + (uint32_t)K::OFF_F * SZ),
-        "l"(pF + (size_t)t * strF), "r"(by_F)
+        "mul.lo.u32 n, %3, %15;\n\t"
+        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
+        "mul.lo.u32 n, %3, %16;\n\tadd.u32 d, %2, %17;\n\t"
+        "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%5], n, [%0];\n\t"
+        "mul.lo.u32 n, %3, %18;\n\tadd.u32 d, %2, %19;\n\t"
+        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%6], n, [%0];\n\t"
+        "mul.lo.u32 n, %3, %20;\n\tadd.u32 d, %2, %21;\n\t"
+        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%7], n, [%0];\n\t"
+        "add.u32 d, %2, %23;\n\t"
+        "@Pf cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%9], n, [%0];\n\t"
+        "mul.lo.u32 n, %3, %22;\n\tadd.u32 d, %2, %24;\n\t"
+        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%8], n, [%0];\n\t"
+        "add.u32 d, %2, %25;\n\t"
+        "@PB cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%10], n, [%0];\n\t"
+        "add.u32 d, %2, %26;\n\t"
+        "@PB cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%11], n, [%0];\n\t"
+        "}" ::"r"(bar),                                                                    // 0
+        "r"(by_base + (needF ? ucnt * (N * P) : 0u) + (needf ? ucnt * N : 0u)),             // 1
+        "r"(dst), "r"(ucnt),                                                                 // 2 3
+        "l"(pC + tB * (P * P)), "l"(pF + tB * (N * P)), "l"(pc + tB * P), "l"(px + tB * N),  // 4 5 6 7
+        "l"(pu + tB * M), "l"(pf + tB * N), "l"(plo + tB * M), "l"(phi + tB * M),            // 8 9 10 11
+        "r"(needF), "r"(needf), "r"(has_tb),                                                 // 12 13 14
+        "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),   // 15..21
+        "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)              // 22..26
         : "memory");
     iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
   };
@@ -240,50 +272,33 @@ lqr_step2_kernel(const StepArgs a) {
   };
   // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
   const int G = T + (a.do_rollout ? T : 0);
-  auto issue_g = [&](int g) { issue(g < T ? T - 1 - g : g - T); };
+  auto issue_g = [&](int g) {
+    if (g < T) issue(T - 1 - g, false);
+    else issue(g - T, true);
+  };
   for (int g = 0; g < S && g < G; ++g) issue_g(g);
 
-  // ------------------------------------------------------------------ small per-step vectors: global -> registers
-  const R* gc = (const R*)a.c;
-  const R* gcx = (const R*)a.cur_x;
-  const R* gcu = (const R*)a.cur_u;
-  const R* gf = (const R*)a.f;
-  const R* glo = (const R*)a.u_lower;
-  const R* ghi = (const R*)a.u_upper;
   const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
-  using Small = SmallTile<R, N, M>;
-  auto fetch = [&](int t, bool fwd, Small& o) {
-    const size_t tb_ = (size_t)t * B + bsafe;
-    R tx[N], tu[M];
-    load_span<R, N, A_N>(gcx + tb_ * N, tx);
-    load_span<R, M, A_M>(gcu + tb_ * M, tu);
-#pragma unroll
-    for (int i = 0; i < N; ++i) o.tb[i] = tx[i];
-#pragma unroll
-    for (int q = 0; q < M; ++q) o.tb[N + q] = tu[q];
-    o.cj = ld_pair<R>(gc + tb_ * P + c0);
-    o.fj = {R(0), R(0)};
-    if (fwd && a.has_f && t < T - 1) o.fj = ld_pair<R>(gf + tb_ * N + xr0);
-    if (BOX && a.bounds_kind == 2) {
-      load_span<R, M, A_M>(glo + tb_ * M, o.lo);
-      load_span<R, M, A_M>(ghi + tb_ * M, o.hi);
-    }
-    o.zm = 0u;
+  auto mask_bits = [&](int t) -> unsigned {               // u_zero_I of (t, problem): M bytes, straight from global
+    unsigned z = 0u;
     if (has_mask) {
 #pragma unroll
-      for (int q = 0; q < M; ++q) o.zm |= (a.zero_mask[tb_ * M + q] ? 1u : 0u) << q;
+      for (int q = 0; q < M; ++q) z |= (a.zero_mask[((size_t)t * B + bsafe) * M + q] ? 1u : 0u) << q;
     }
+    return z;
   };
 
   // per-problem element offsets inside a stage
   const int oC = K::OFF_C + pi * P * P, oF = K::OFF_F + pi * N * P;
+  const int oc = K::OFF_c + pi * P, of_ = K::OFF_f + pi * N, ox = K::OFF_x + pi * N, ou = K::OFF_u + pi * M;
+  const int olo = K::OFF_lo + pi * M, ohi = K::OFF_hi + pi * M;
   R* scr = scratch + (size_t)pi * K::SCRS;
   R* Vs = scr + K::SC_V;
   R* vs = scr + K::SC_v;
   R* Qx = scr + K::SC_Q;
   R* xs = scr + K::SC_X;
   R* red = scr + K::SC_R;
-  R* kst = a.k_in_smem ? kstore + (size_t)pi * T * KT : scr + K::SC_K;
+  R* kst = KSM ? kstore + (size_t)pi * T * KT : scr + K::SC_K;
   R* gKs = (R*)a.Ks;
   R* gks = (R*)a.ks;
   const R s_lo = (R)a.u_lo, s_hi = (R)a.u_hi, s_du = (R)a.delta_u, decay = (R)a.ls_decay;
@@ -307,39 +322,40 @@ lqr_step2_kernel(const StepArgs a) {
   P2<R> Fp[N];                                     // (F[k][c0], F[k][c0+1])
   R ubar[M], blo[M], bhi[M];                       // u_bar_t and tensor bounds of the step being solved
   unsigned zmk = 0u;
-  Small sA, sB;                                    // small vectors of steps t-1 and t-2
-  // the V-independent part of step tt, from tile `stt` and small vectors `sm`
-  auto pre = [&](int tt, const R* stt, const Small& sm) {
+  // the V-independent part of step tt, from its tile `stt`
+  auto pre = [&](int tt, const R* stt) {
 #pragma unroll
     for (int i = 0; i < P; ++i) Qp[i] = ld_pair<R>(stt + oC + i * P + c0);
-    R Cr0[P], Cr1[P];
+    R Cr0[P], Cr1[P], tb[P];
     load_span<R, P, EA>(stt + oC + c0 * P, Cr0);            // c0 * P is a multiple of 4
     load_span<R, P, 2>(stt + oC + (c0 + 1) * P, Cr1);
-    R ct0, ct1;
-    dot2_span<R, P>(Cr0, Cr1, sm.tb, ct0, ct1);              // rows c0, c0+1 of C tau_bar (lqr_step.py:289-295)
-    R tj0 = sm.tb[0], tj1 = sm.tb[1];              // tau_bar[c0], tau_bar[c0+1] (c0 is lane dependent: select)
+    {
+      R tx[N], tu[M];
+      load_span<R, N, A_N>(stt + ox, tx);
+      load_span<R, M, A_M>(stt + ou, tu);
 #pragma unroll
-    for (int i = 2; i < P; i += 2)
-      if (c0 == i) { tj0 = sm.tb[i]; tj1 = sm.tb[i + 1]; }
-    if (writer_lane) oldcost_part += tj0 * (R(0.5) * ct0 + sm.cj.x) + tj1 * (R(0.5) * ct1 + sm.cj.y);   // util.get_cost (:169)
-    qp = {ct0 + sm.cj.x, ct1 + sm.cj.y};
+      for (int i = 0; i < N; ++i) tb[i] = tx[i];
+#pragma unroll
+      for (int q = 0; q < M; ++q) tb[N + q] = tu[q];
+    }
+    const P2<R> cj = ld_pair<R>(stt + oc + c0);
+    const P2<R> tj = ld_pair<R>(stt + (isx ? ox + c0 : ou + ua0));   // tau_bar[c0], tau_bar[c0+1]
+    R ct0, ct1;
+    dot2_span<R, P>(Cr0, Cr1, tb, ct0, ct1);                 // rows c0, c0+1 of C tau_bar (lqr_step.py:289-295)
+    if (writer_lane) oldcost_part += tj.x * (R(0.5) * ct0 + cj.x) + tj.y * (R(0.5) * ct1 + cj.y);   // util.get_cost (:169)
+    qp = {ct0 + cj.x, ct1 + cj.y};
 #pragma unroll
     for (int q = 0; q < M; ++q) {
-      ubar[q] = sm.tb[N + q];
-      if (BOX && a.bounds_kind == 2) { blo[q] = sm.lo[q]; bhi[q] = sm.hi[q]; }
+      ubar[q] = tb[N + q];
+      if (BOX && a.bounds_kind == 2) {
+        blo[q] = stt[olo + q];
+        bhi[q] = stt[ohi + q];
+      }
     }
-    zmk = sm.zm;
-    (void)tt;
+    zmk = mask_bits(tt);
   };
-  const R* st;
-  {
-    Small s0;
-    fetch(T - 1, false, s0);
-    if (T > 1) fetch(T - 2, false, sA);
-    if (T > 2) fetch(T - 3, false, sB);
-    st = acquire(0u);
-    pre(T - 1, st, s0);
-  }
+  const R* st = acquire(0u);
+  pre(T - 1, st);
   for (int t = T - 1; t >= 0; --t) {
 #ifdef MPCB2_TIMING
     ck0 = clock64();
@@ -374,7 +390,7 @@ lqr_step2_kernel(const StepArgs a) {
       for (int k = 0; k < N; ++k) qp = fma2s(Fp[k], vv[k], qp);
     }
     TICK2(tk, 2)
-    // tile t is consumed (its C pair / rows were read by pre(t)): refill the stage with tile g + S
+    // tile t is consumed (its C pair / rows / vectors were read by pre(t)): refill the stage with tile g + S
     __syncwarp();
     {
       const int g = (T - 1 - t) + S;
@@ -453,7 +469,7 @@ lqr_step2_kernel(const StepArgs a) {
     TICK2(tk, 4)
     // K[:, pair] = -Hff^{-1} Qux_f[:, pair] (rows of clamped / masked controls are zero)
     P2<R> Kp[M];
-    R* Kt = a.k_in_smem ? kst + (size_t)t * KT : kst;
+    R* Kt = KSM ? kst + (size_t)t * KT : kst;
     {
       R r0[M], r1[M], s0[M], s1[M];
 #pragma unroll
@@ -468,7 +484,7 @@ lqr_step2_kernel(const StepArgs a) {
       for (int q = 0; q < M; ++q) Kp[q] = {-s0[q], -s1[q]};
     }
     // publish: x lanes their K pair (rows of the gain store), u lanes their Q_xu pair as rows [i][a] -
-    // one predicated store sequence for both kinds of lanes (no divergent branches)
+    // one predicated store sequence for both kinds of lanes
     {
       R* sbase = isx ? Kt + c0 : Qx + ua0;
       const int sstr = isx ? NV : M;
@@ -552,9 +568,7 @@ lqr_step2_kernel(const StepArgs a) {
     TICK2(tk, 6)
     // V-independent part of step t-1, in the shadow of the V round trip through shared memory
     if (t > 0) {
-      pre(t - 1, st_next, sA);
-      sA = sB;
-      if (t >= 3) fetch(t - 3, false, sB);
+      pre(t - 1, st_next);
       st = st_next;
     }
     __syncwarp();
@@ -576,8 +590,8 @@ lqr_step2_kernel(const StepArgs a) {
 
   // ======================= rollout + line search (lqr_step.py:164-261) =======================
   // Per step the dependent chain is x -> u = K dx + .. -> clamp -> x' = F tau + f -> exchange.  The operands
-  // of step t+1 (gain rows, rows of C and F) are loaded into the registers of step t as soon as those are
-  // dead, so they are in flight while the chain of step t runs.
+  // of step t+1 (gain rows, rows of C and F, the small vectors) are loaded into the registers of step t as
+  // soon as those are dead, so they are in flight while the chain of step t runs.
   const R* gx0 = (const R*)a.x_init;
   R* gnx = (R*)a.new_x;
   R* gnu = (R*)a.new_u;
@@ -586,39 +600,55 @@ lqr_step2_kernel(const StepArgs a) {
   bool worse = false;
   for (int pass = 0;; ++pass) {
     if (pass > 0) {                                // line-search repeat: restart this warp's tile stream
-      for (int g = 0; g < S && g < T; ++g) issue(g);
+      for (int g = 0; g < S && g < T; ++g) issue(g, true);
     }
-    Small sm0;                                     // steps t, t+1, t+2
-    fetch(0, true, sm0);
-    if (T > 1) fetch(1, true, sA);
-    if (T > 2) fetch(2, true, sB);
     R xr[N];                                       // state replicated on every lane
     load_span<R, N, A_N>(gx0 + (size_t)bsafe * N, xr);
     P2<R> xown = ld_pair<R>(gx0 + (size_t)bsafe * N + xr0);
-    R Krow[M][N], kq[M], Cr0[P], Cr1[P], Fr0[P], Fr1[P];
+    R Krow[M][N], kq[M], Cr0[P], Cr1[P], Fr0[P], Fr1[P], tbx[N], tbu[M], lo_t[M], hi_t[M];
+    P2<R> cj, fj;
+    unsigned zm = 0u;
     auto load_gain = [&](int tt) {
-      const R* Kt = kst + (size_t)tt * KT;
-      const size_t row = (size_t)tt * B + bsafe;
+      if constexpr (KSM) {
+        const R* Kt = kst + (size_t)tt * KT;
 #pragma unroll
-      for (int q = 0; q < M; ++q) {
-        if (a.k_in_smem) {
+        for (int q = 0; q < M; ++q) {
           load_span<R, N, EA>(Kt + q * NV, Krow[q]);
           kq[q] = Kt[M * NV + q];
-        } else {
+        }
+      } else {
+        const size_t row = (size_t)tt * B + bsafe;
 #pragma unroll
-          for (int i = 0; i < N; ++i) Krow[q][i] = __ldcg(gKs + (row * M + q) * N + i);
-          kq[q] = __ldcg(gks + row * M + q);
+        for (int q = 0; q < M; ++q) {
+          load_span<R, N, A_N>(gKs + (row * M + q) * N, Krow[q]);
+          kq[q] = gks[row * M + q];
         }
       }
     };
+    auto load_tile = [&](int tt, const R* stt) {   // rows c0, c0+1 of C and F, nominal point, c, f, bounds
+      load_span<R, P, EA>(stt + oC + c0 * P, Cr0);
+      load_span<R, P, 2>(stt + oC + (c0 + 1) * P, Cr1);
+      if (tt < T - 1) {
+        load_span<R, P, EA>(stt + oF + xr0 * P, Fr0);
+        load_span<R, P, 2>(stt + oF + (xr0 + 1) * P, Fr1);
+      }
+      load_span<R, N, A_N>(stt + ox, tbx);
+      load_span<R, M, A_M>(stt + ou, tbu);
+      cj = ld_pair<R>(stt + oc + c0);
+      fj = {R(0), R(0)};
+      if (a.has_f && tt < T - 1) fj = ld_pair<R>(stt + of_ + xr0);
+      if (BOX && a.bounds_kind == 2) {
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+          lo_t[q] = stt[olo + q];
+          hi_t[q] = stt[ohi + q];
+        }
+      }
+      zm = mask_bits(tt);
+    };
     st = acquire(0u);
     load_gain(0);
-    load_span<R, P, EA>(st + oC + c0 * P, Cr0);
-    load_span<R, P, 2>(st + oC + (c0 + 1) * P, Cr1);
-    if (T > 1) {
-      load_span<R, P, EA>(st + oF + xr0 * P, Fr0);
-      load_span<R, P, 2>(st + oF + (xr0 + 1) * P, Fr1);
-    }
+    load_tile(0, st);
     R cpart = R(0), dun2 = R(0);
     size_t orow = (size_t)bsafe;                   // t*B + b
     for (int t = 0; t < T; ++t, orow += (size_t)B) {
@@ -627,31 +657,31 @@ lqr_step2_kernel(const StepArgs a) {
 #endif
       uint32_t ok_next = 0u;
       if (t + 1 < T) ok_next = probe();            // tile t+1
-      const R (&tb)[P] = sm0.tb;
       R dxv[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) dxv[i] = xr[i] - tb[i];
+      for (int i = 0; i < N; ++i) dxv[i] = xr[i] - tbx[i];
       R u[M];
 #pragma unroll
-      for (int q = 0; q < M; ++q) u[q] = (dot_span<R, N>(Krow[q], dxv) + tb[N + q]) + alpha * kq[q];   // (:192)
+      for (int q = 0; q < M; ++q) u[q] = (dot_span<R, N>(Krow[q], dxv) + tbu[q]) + alpha * kq[q];   // (:192)
       if (t + 1 < T) load_gain(t + 1);             // gain registers are dead: fetch the next step's rows
+      P2<R> ubj = {tbu[0], tbu[1]};
 #pragma unroll
       for (int q = 0; q < M; ++q) {
         if constexpr (MODE != MODE_PLAIN) {
-          if (has_mask && ((sm0.zm >> q) & 1u)) u[q] = R(0);                // (:197-198)
+          if (has_mask && ((zm >> q) & 1u)) u[q] = R(0);                    // (:197-198)
         }
         if constexpr (BOX) {                                                // (:200-213)
-          R lo = a.bounds_kind == 2 ? sm0.lo[q] : s_lo;
-          R hi = a.bounds_kind == 2 ? sm0.hi[q] : s_hi;
+          R lo = a.bounds_kind == 2 ? lo_t[q] : s_lo;
+          R hi = a.bounds_kind == 2 ? hi_t[q] : s_hi;
           if (a.has_delta) {
-            const R l2 = tb[N + q] - s_du, h2 = tb[N + q] + s_du;
+            const R l2 = tbu[q] - s_du, h2 = tbu[q] + s_du;
             lo = l2 < lo ? lo : l2;
             hi = h2 > hi ? hi : h2;
           }
           u[q] = u[q] < lo ? lo : u[q];                                       // util.eclamp: lower, then upper
           u[q] = u[q] > hi ? hi : u[q];
         }
-        const R d = tb[N + q] - u[q];
+        const R d = tbu[q] - u[q];
         dun2 += d * d;
       }
       TICK2(tf, 1)
@@ -662,25 +692,24 @@ lqr_step2_kernel(const StepArgs a) {
       for (int q = 0; q < M; ++q) tau[N + q] = u[q];
       // own pair of tau: x lanes carry it, u lanes pick their controls
       P2<R> tj = xown;
-      P2<R> ubj = {tb[N], tb[N + 1]};
       if (!isx) {
 #pragma unroll
         for (int q = 0; q < M; q += 2)
           if (q == ua0) {
             tj = {u[q], u[q + 1]};
-            ubj = {tb[N + q], tb[N + q + 1]};
+            ubj = {tbu[q], tbu[q + 1]};
           }
       }
       P2<R> xn = {R(0), R(0)};
       if (t < T - 1) {                                                        // (:217-222) - the chain first
         dot2_span<R, P>(Fr0, Fr1, tau, xn.x, xn.y);
-        xn.x += sm0.fj.x;
-        xn.y += sm0.fj.y;
+        xn.x += fj.x;
+        xn.y += fj.y;
         if (writer_lane && isx) st_pair(xs + (t & 1) * NV + c0, xn);
       }
       R ct0, ct1;
       dot2_span<R, P>(Cr0, Cr1, tau, ct0, ct1);
-      if (writer_lane) cpart += tj.x * (R(0.5) * ct0 + sm0.cj.x) + tj.y * (R(0.5) * ct1 + sm0.cj.y);   // (:232)
+      if (writer_lane) cpart += tj.x * (R(0.5) * ct0 + cj.x) + tj.y * (R(0.5) * ct1 + cj.y);   // (:232)
       if (wr) {
         if (isx) {
           st_pair(gnx + orow * N + c0, tj);
@@ -690,26 +719,18 @@ lqr_step2_kernel(const StepArgs a) {
         }
       }
       TICK2(tf, 2)
-      // rows of C and F of step t+1 into the (now dead) registers of step t
+      // operands of step t+1 into the (now dead) registers of step t
       const R* st_next = st;
       if (t + 1 < T) {
         st_next = acquire(ok_next);
-        load_span<R, P, EA>(st_next + oC + c0 * P, Cr0);
-        load_span<R, P, 2>(st_next + oC + (c0 + 1) * P, Cr1);
-        if (t + 2 < T) {
-          load_span<R, P, EA>(st_next + oF + xr0 * P, Fr0);
-          load_span<R, P, 2>(st_next + oF + (xr0 + 1) * P, Fr1);
-        }
+        load_tile(t + 1, st_next);
       }
       xown = xn;
       __syncwarp();
       if (t < T - 1) load_span<R, N, EA>(xs + (t & 1) * NV, xr);
       TICK2(tf, 3)
-      sm0 = sA;
-      sA = sB;
-      if (t + 3 < T) fetch(t + 3, true, sB);
-      // tile t is consumed (its rows were loaded one step ago): refill its stage
-      if (t + S < T) issue(t + S);
+      // tile t is consumed (its operands were loaded one step ago): refill its stage
+      if (t + S < T) issue(t + S, true);
       st = st_next;
       TICK2(tf, 4)
     }
@@ -757,11 +778,17 @@ int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t str
     if (smem > (size_t)max_smem_optin) return 4;
     if (a.do_rollout && !have_ws) return 4;
   }
-  auto kern = lqr_step2_kernel<R, N, M, MODE>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
   const int warps = (a.B + K::PPW - 1) / K::PPW;
   const int grid = (warps + K::NW - 1) / K::NW;
-  kern<<<grid, K::NW * 32, smem, stream>>>(a);
+  if (a.k_in_smem) {
+    auto kern = lqr_step2_kernel<R, N, M, MODE, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
+    kern<<<grid, K::NW * 32, smem, stream>>>(a);
+  } else {
+    auto kern = lqr_step2_kernel<R, N, M, MODE, false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
+    kern<<<grid, K::NW * 32, smem, stream>>>(a);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 5;
 }
 
