@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCB200_VERSION 1
+#define MPCB200_VERSION 2
 
 enum {
   MPCB200_OK = 0,
@@ -58,13 +58,23 @@ typedef struct mpcb200_dims {
   int32_t pnqp_max_iter;  /* projected-Newton iteration cap (reference: 20)            */
   int32_t do_rollout;     /* 1: Riccati sweep + line-search rollout (LinDx/QuadCost)
                              0: Riccati sweep only; Ks/ks must be given                */
+  int32_t dynamics_kind;  /* true dynamics of the rollout (reference lqr_step.py:217-225):
+                             MPCB200_DYN_LINEAR = LinDx(F,f); MPCB200_DYN_CARTPOLE / _PENDULUM = the step
+                             function of that system evaluated inside the kernel (params.dyn); F,f are
+                             then its linearisation and are used by the Riccati sweep only (ABI v2)  */
 } mpcb200_dims;
 
 typedef struct mpcb200_params {
   double u_lo, u_hi;      /* scalar bounds (bounds_kind == 1)   */
   double delta_u;         /* has_delta_u                        */
   double ls_decay;        /* linesearch_decay                   */
+  double dyn[8];          /* parameters of a known system (dims.dynamics_kind != 0), see mpcb200_dyn_* (ABI v2) */
 } mpcb200_params;
+
+/* Known nonlinear systems (reference mpc/env_dx/cartpole.py:63-96, mpc/env_dx/pendulum.py:49-84).
+ * dyn[] = cartpole: gravity, masscart, masspole, length, force_mag, dt   (state x,dx,cos th,sin th,dth; n=5, m=1)
+ *         pendulum: g, m, l, (unused), max_torque, dt                    (state cos th,sin th,dth; n=3, m=1) */
+enum { MPCB200_DYN_LINEAR = 0, MPCB200_DYN_CARTPOLE = 1, MPCB200_DYN_PENDULUM = 2 };
 
 /* Per-problem status bits written to `status[B]`. */
 #define MPCB200_ST_PNQP_UNCONVERGED 1u /* some time step hit pnqp_max_iter (reference prints a warning, pnqp.py:81) */
@@ -146,6 +156,25 @@ int mpcb200_rollout_f32(const mpcb200_dims* dims, const float* F, const float* f
                         const float* u, float* x, void* stream);
 int mpcb200_rollout_f64(const mpcb200_dims* dims, const double* F, const double* f, const double* x_init,
                         const double* u, double* x, void* stream);
+
+/*
+ * Known nonlinear dynamics on the device.
+ *   mpcb200_dyn_rollout_*:   x[0] = x_init, x[t+1] = step(x[t], u[t])  - util.get_traj for a Module
+ *                            (reference mpc/util.py:102-126 with dynamics(x,u), one Python call per step).
+ *   mpcb200_dyn_linearize_*: F[t,b] = [d step/dx, d step/du], f[t,b] = step(x,u) - F [x;u] at (x[t,b], u[t,b]),
+ *                            t < T-1 - linearize_dynamics (reference mpc/mpc.py:490-601; its AUTO_DIFF mode does
+ *                            (T-1)*n_state autograd passes).  Exact Jacobians by forward-mode dual numbers.
+ * kind = MPCB200_DYN_CARTPOLE | MPCB200_DYN_PENDULUM; dyn = HOST pointer to 8 doubles (see mpcb200_params.dyn);
+ * x_init[B,n] u[T,B,m] x[T,B,n] F[T-1,B,n,n+m] f[T-1,B,n]; n, m are those of the system.
+ */
+int mpcb200_dyn_rollout_f32(int32_t kind, const double* dyn, int32_t B, int32_t T, const float* x_init,
+                            const float* u, float* x, void* stream);
+int mpcb200_dyn_rollout_f64(int32_t kind, const double* dyn, int32_t B, int32_t T, const double* x_init,
+                            const double* u, double* x, void* stream);
+int mpcb200_dyn_linearize_f32(int32_t kind, const double* dyn, int32_t B, int32_t T, const float* x,
+                              const float* u, float* F, float* f, void* stream);
+int mpcb200_dyn_linearize_f64(int32_t kind, const double* dyn, int32_t B, int32_t T, const double* x,
+                              const double* u, double* F, double* f, void* stream);
 
 /*
  * Standalone projected-Newton box QP, n <= 8: replaces pnqp(H,q,lower,upper,x_init,n_iter) of the

@@ -16,11 +16,11 @@ LIB_PATH = os.environ.get("MPCB200_LIB", os.path.join(_HERE, "libmpcb200.so"))  
 class Dims(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in (
         "B", "T", "n", "m", "F_T", "has_f", "bounds_kind", "has_zero_mask",
-        "has_delta_u", "max_ls_iter", "pnqp_max_iter", "do_rollout")]
+        "has_delta_u", "max_ls_iter", "pnqp_max_iter", "do_rollout", "dynamics_kind")]
 
 
 class Params(ctypes.Structure):
-    _fields_ = [(k, ctypes.c_double) for k in ("u_lo", "u_hi", "delta_u", "ls_decay")]
+    _fields_ = [(k, ctypes.c_double) for k in ("u_lo", "u_hi", "delta_u", "ls_decay")] + [("dyn", ctypes.c_double * 8)]
 
 
 class MpcB200Error(RuntimeError):
@@ -33,6 +33,7 @@ _lib = None
 EXPORTED_SYMBOLS = (
     "mpcb200_lqr_step_f32", "mpcb200_lqr_step_f64", "mpcb200_lqr_grad_f32", "mpcb200_lqr_grad_f64",
     "mpcb200_rollout_f32", "mpcb200_rollout_f64", "mpcb200_pnqp_f32", "mpcb200_pnqp_f64",
+    "mpcb200_dyn_rollout_f32", "mpcb200_dyn_rollout_f64", "mpcb200_dyn_linearize_f32", "mpcb200_dyn_linearize_f64",
     "mpcb200_supported", "mpcb200_supported_list", "mpcb200_launch_count",
     "mpcb200_step_smem_bytes", "mpcb200_step_prefers_workspace", "mpcb200_version", "mpcb200_strerror",
 )
@@ -66,6 +67,14 @@ def lib():
     for name in ("mpcb200_pnqp_f32", "mpcb200_pnqp_f64"):
         fn = getattr(L, name)
         fn.argtypes = [ctypes.c_int32, ctypes.c_int32] + [vp] * 5 + [ctypes.c_int32] + [vp] * 6
+        fn.restype = ctypes.c_int
+    for name in ("mpcb200_dyn_rollout_f32", "mpcb200_dyn_rollout_f64"):
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.c_int32] + [vp] * 4
+        fn.restype = ctypes.c_int
+    for name in ("mpcb200_dyn_linearize_f32", "mpcb200_dyn_linearize_f64"):
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.c_int32] + [vp] * 5
         fn.restype = ctypes.c_int
     L.mpcb200_supported.argtypes = [ctypes.c_int32, ctypes.c_int32]
     L.mpcb200_supported.restype = ctypes.c_int

@@ -132,6 +132,13 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
   ok = ok && (x_init == nullptr || aligned16(x_init));
   ok = ok && ((size_t)d->B * d->m * sz) % 16 == 0 && ((size_t)d->B * d->n * sz) % 16 == 0;
   a.bulk_ok = ok ? 1 : 0;
+  a.dyn_kind = d->dynamics_kind;
+  if (a.dyn_kind != DYN_LINEAR) {
+    const bool shape_ok = (a.dyn_kind == DYN_CARTPOLE && d->n == 5 && d->m == 1) ||
+                          (a.dyn_kind == DYN_PENDULUM && d->n == 3 && d->m == 1);
+    if (!shape_ok) return MPCB200_ERR_BAD_DIMS;
+    for (int i = 0; i < 8; ++i) a.dp.p[i] = p->dyn[i];
+  }
   if (const char* k = std::getenv("MPCB200_KERNEL")) a.impl = std::atoi(k);   // developer A/B knob: 1 generic, 2 pair
   rc = (sizeof(R) == 4 ? e->step32 : e->step64)(a, smem, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(1);
@@ -177,6 +184,30 @@ static int rollout_impl(const mpcb200_dims* d, const R* F, const R* f, const R* 
   a.F = F; a.f = f; a.x_init = x_init; a.u = u; a.x = x;
   rc = (sizeof(R) == 4 ? e->roll32 : e->roll64)(a, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(1);
+  return rc;
+}
+template <typename R>
+static int dyn_impl(bool linearize, int kind, const double* dyn, int B, int T, const R* x_or_init, const R* u,
+                    R* x_out, R* F, R* f, void* stream) {
+  if (dyn == nullptr || x_or_init == nullptr || u == nullptr) return MPCB200_ERR_NULL_POINTER;
+  if (B <= 0 || T <= 0 || (kind != DYN_CARTPOLE && kind != DYN_PENDULUM)) return MPCB200_ERR_BAD_DIMS;
+  if (max_smem_optin() <= 0) return MPCB200_ERR_NO_DEVICE;
+  DynArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.B = B; a.T = T; a.kind = kind;
+  for (int i = 0; i < 8; ++i) a.dp.p[i] = dyn[i];
+  a.u = u;
+  int rc;
+  if (linearize) {
+    if (T > 1 && (F == nullptr || f == nullptr)) return MPCB200_ERR_NULL_POINTER;
+    a.x = x_or_init; a.F = F; a.f = f;
+    rc = launch_dyn_linearize<R>(a, (cudaStream_t)stream);
+  } else {
+    if (x_out == nullptr) return MPCB200_ERR_NULL_POINTER;
+    a.x_init = x_or_init; a.x_out = x_out;
+    rc = launch_dyn_rollout<R>(a, (cudaStream_t)stream);
+  }
+  if (rc == 0 && !(linearize && T == 1)) g_launches.fetch_add(1);
   return rc;
 }
 }  // namespace mpcb200
@@ -225,6 +256,23 @@ int mpcb200_rollout_f32(const mpcb200_dims* dims, const float* F, const float* f
 int mpcb200_rollout_f64(const mpcb200_dims* dims, const double* F, const double* f, const double* x_init,
                         const double* u, double* x, void* stream) {
   return rollout_impl<double>(dims, F, f, x_init, u, x, stream);
+}
+
+int mpcb200_dyn_rollout_f32(int32_t kind, const double* dyn, int32_t B, int32_t T, const float* x_init,
+                            const float* u, float* x, void* stream) {
+  return dyn_impl<float>(false, kind, dyn, B, T, x_init, u, x, nullptr, nullptr, stream);
+}
+int mpcb200_dyn_rollout_f64(int32_t kind, const double* dyn, int32_t B, int32_t T, const double* x_init,
+                            const double* u, double* x, void* stream) {
+  return dyn_impl<double>(false, kind, dyn, B, T, x_init, u, x, nullptr, nullptr, stream);
+}
+int mpcb200_dyn_linearize_f32(int32_t kind, const double* dyn, int32_t B, int32_t T, const float* x,
+                              const float* u, float* F, float* f, void* stream) {
+  return dyn_impl<float>(true, kind, dyn, B, T, x, u, nullptr, F, f, stream);
+}
+int mpcb200_dyn_linearize_f64(int32_t kind, const double* dyn, int32_t B, int32_t T, const double* x,
+                              const double* u, double* F, double* f, void* stream) {
+  return dyn_impl<double>(true, kind, dyn, B, T, x, u, nullptr, F, f, stream);
 }
 
 int mpcb200_supported(int32_t n_state, int32_t n_ctrl) { return find(n_state, n_ctrl) != nullptr; }

@@ -31,6 +31,7 @@
 #pragma once
 #include <cstdio>
 #include "common.cuh"
+#include "dynamics.cuh"
 
 #ifndef MPCB_STAGES
 #define MPCB_STAGES 3
@@ -52,6 +53,8 @@ struct StepArgs {
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
   int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh)
+  int dyn_kind;   // true dynamics of the rollout: DYN_LINEAR (F,f) or a known system evaluated in the kernel
+  DynParams dp;
 };
 
 template <typename R, int N, int M>
@@ -766,11 +769,27 @@ MPCB_DEV void step_consumer(const StepArgs& a, unsigned char* stage_base, uint64
           }
         }
         xn[sl] = R(0);
-        if (t < T - 1) {                                          // (:217-222)
-          Vec<R, P> Frow;
-          Frow.template load<A_ROW>(st + oF + fr[sl] * P);
-          xn[sl] = Frow.dot(tau);
-          if (a.has_f) xn[sl] += st[of_ + fr[sl]];
+        if (t < T - 1) {                                          // (:217-222), or true_dynamics(x, u) (:224-225)
+          bool known = false;
+          if constexpr (M == 1 && (N == DynDims<DYN_CARTPOLE>::N || N == DynDims<DYN_PENDULUM>::N)) {
+            if (a.dyn_kind != DYN_LINEAR) {       // every lane evaluates the step function and keeps its row
+              known = true;
+              R sv[N], ov[N];
+#pragma unroll
+              for (int i = 0; i < N; ++i) sv[i] = tau.get(i);
+              dyn_step<R, N == DynDims<DYN_CARTPOLE>::N ? DYN_CARTPOLE : DYN_PENDULUM, R>(a.dp, sv, tau.get(N), ov);
+              xn[sl] = ov[0];
+#pragma unroll
+              for (int i = 1; i < N; ++i)
+                if (fr[sl] == i) xn[sl] = ov[i];
+            }
+          }
+          if (!known) {
+            Vec<R, P> Frow;
+            Frow.template load<A_ROW>(st + oF + fr[sl] * P);
+            xn[sl] = Frow.dot(tau);
+            if (a.has_f) xn[sl] += st[of_ + fr[sl]];
+          }
         }
       }
       if (t < T - 1) {

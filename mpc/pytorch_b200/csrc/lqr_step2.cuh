@@ -111,6 +111,11 @@ struct Step2Cfg {
   // n, m) and per-problem vectors that the lanes read straight from global memory with vector loads
   static constexpr bool OK = (N % 2 == 0) && (M % 2 == 0) && L <= 16 && N >= 2 && M >= 2 && (PPW * M * SZ) % 16 == 0 &&
                              (PPW * N * SZ) % 16 == 0 && (PPW * P * SZ) % 16 == 0;
+  // default choice between this mapping and the generic kernel, from measurements on B200 (profiles/
+  // r02_shapes_generic_vs_pair.log): the pair mapping wins where the dense products dominate (n+m >= 18:
+  // 1.5-1.8x at n=16, m=4) and for narrow problems (n+m <= 6, where 10+ problems share a warp); in between
+  // (n=8, m=2: 39 vs 37 us at config 3) the step is latency bound either way and the generic kernel stays.
+  static constexpr bool PAIR_DEFAULT = OK && (P >= 18 || P <= 6 || (N == 8 && M == 4));
   // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + PPW * P * P;

@@ -44,6 +44,11 @@ def _mv(A, x):
 def get_traj(T, u, x_init, dynamics):
     """Nominal rollout under the true dynamics (reference mpc/util.py:102-126), no graph."""
     with torch.no_grad():
+        if isinstance(dynamics, Module):
+            from .dynamics import known_kind, dyn_rollout_raw
+            kind, kparams = known_kind(dynamics, x_init.shape[1], u.shape[2], x_init)
+            if kind:                                          # one kernel instead of T-1 Module calls
+                return dyn_rollout_raw(kind, kparams, T, _detach(x_init), _detach(u))
         xs = [_detach(x_init)]
         if isinstance(dynamics, LinDx):
             F, f = _detach(dynamics.F), _detach(dynamics.f)
@@ -220,15 +225,16 @@ class MPC(Module):
             else:
                 C, c, _ = self.approximate_cost(x, u, cost, diff=False)
 
+            defer = {} if self.verbose <= 0 else None       # step counters stay on the device unless they are printed
             x, u, n_total_qp_iter, costs, full_du_norm, mean_alphas = \
-                self.solve_lqr_subproblem(x_init, C, c, F, f, cost, dx, x, u)
+                self.solve_lqr_subproblem(x_init, C, c, F, f, cost, dx, x, u, _defer_host=defer)
             n_not_improved += 1
             assert x.ndimension() == 3 and u.ndimension() == 3
 
             # best-iterate tracking on the device (reference :271-285 semantics per element)
             if best is None:
                 best = {"x": x, "u": u, "costs": costs, "full_du_norm": full_du_norm}
-                flags = torch.stack((full_du_norm.max(), torch.zeros_like(full_du_norm[0])))
+                flags = [full_du_norm.max(), torch.zeros_like(full_du_norm[0])]
             else:
                 better = costs <= best["costs"] + self.best_cost_eps
                 sel = better.view(1, -1, 1)
@@ -236,8 +242,13 @@ class MPC(Module):
                         "u": torch.where(sel, u, best["u"]),
                         "costs": torch.where(better, costs, best["costs"]),
                         "full_du_norm": torch.where(better, full_du_norm, best["full_du_norm"])}
-                flags = torch.stack((full_du_norm.max(), better.any().to(full_du_norm.dtype)))
-            max_du, any_better = flags.tolist()             # the one host sync of this iteration
+                flags = [full_du_norm.max(), better.any().to(full_du_norm.dtype)]
+            if defer:
+                flags.append(defer["unconverged"].to(full_du_norm.dtype))
+            vals = torch.stack(flags).tolist()              # the one host sync of this iteration
+            max_du, any_better = vals[0], vals[1]
+            if defer and vals[2] and self.verbose >= 0:
+                print("[WARNING] pnqp warning: Did not converge")   # reference pnqp.py:81
             if any_better:
                 n_not_improved = 0
 
@@ -284,7 +295,16 @@ class MPC(Module):
         return (x, u, best["costs"])
 
     # ------------------------------------------------------------------------------------
-    def solve_lqr_subproblem(self, x_init, C, c, F, f, cost, dynamics, x, u, no_op_forward=False):
+    def solve_lqr_subproblem(self, x_init, C, c, F, f, cost, dynamics, x, u, no_op_forward=False,
+                             _defer_host=None):
+        from .step import _host_reads
+        _host_reads.defer = _defer_host
+        try:
+            return self._solve_lqr_subproblem(x_init, C, c, F, f, cost, dynamics, x, u, no_op_forward)
+        finally:
+            _host_reads.defer = None
+
+    def _solve_lqr_subproblem(self, x_init, C, c, F, f, cost, dynamics, x, u, no_op_forward=False):
         n, m, T = self.n_state, self.n_ctrl, self.T
         common = dict(T=T, u_lower=self.u_lower, u_upper=self.u_upper, u_zero_I=self.u_zero_I,
                       delta_u=self.delta_u, linesearch_decay=self.linesearch_decay,
@@ -368,6 +388,11 @@ class MPC(Module):
         evaluated for all T-1 steps and the whole batch at once."""
         T, n, m = self.T, self.n_state, self.n_ctrl
         B = x.shape[1]
+        if not diff and self.grad_method in (GradMethods.ANALYTIC, GradMethods.AUTO_DIFF):
+            from .dynamics import known_kind, dyn_linearize_raw
+            kind, kparams = known_kind(dynamics, n, m, x)
+            if kind:           # exact Jacobians of a known system by forward-mode duals, one kernel
+                return dyn_linearize_raw(kind, kparams, T, x, u)
         xs = x[:-1].detach().reshape(-1, n)
         us = u[:-1].detach().reshape(-1, m)
         if self.grad_method == GradMethods.ANALYTIC:

@@ -6,6 +6,7 @@ shapes, and the same gradient tuple ``(dx_init, dC, dc, dF, df)`` (:407).  The
 arithmetic runs in csrc/lqr_step.cuh and csrc/lqr_grad.cuh.
 """
 import ctypes
+import threading
 
 import torch
 from torch.autograd import Function
@@ -15,6 +16,11 @@ from . import _lib
 from ._lib import Dims, Params, MpcB200Error, check, ptr, stream_handle
 
 PNQP_MAX_ITER = 20  # reference passes n_iter=20 (mpc/lqr_step.py:137)
+
+# MPC's loop sets `_host_reads.defer` to a dict around its LQRStep calls: the per-step pnqp counters then stay
+# on the device (no .item() per step) and MPC reads them with its own stop-test scalars.  Thread local; the
+# LQRStep(...) signature itself stays the reference's.
+_host_reads = threading.local()
 
 
 def _is_empty(t):
@@ -136,7 +142,7 @@ class _on_device:
 def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
                  u_lower=None, u_upper=None, u_zero_I=None, delta_u=None,
                  linesearch_decay=0.2, max_linesearch_iter=10, do_rollout=True,
-                 want_gains=False, want_stats=True, want_du_first=False):
+                 want_gains=False, want_stats=True, want_du_first=False, dyn=None):
     """Run the step kernel.  Returns a dict of device tensors:
     new_x,new_u,costs,full_du_norm,alphas (do_rollout) and, on request, Ks,ks,qp_iters,
     free_mask,status."""
@@ -228,7 +234,9 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     dims = Dims(B=B, T=T, n=N, m=M, F_T=F_T, has_f=int(f_ is not None), bounds_kind=bounds_kind,
                 has_zero_mask=int(zmask is not None), has_delta_u=int(delta_u is not None),
                 max_ls_iter=int(max_linesearch_iter), pnqp_max_iter=PNQP_MAX_ITER,
-                do_rollout=int(bool(do_rollout)))
+                do_rollout=int(bool(do_rollout)), dynamics_kind=int(dyn[0]) if dyn is not None else 0)
+    if dyn is not None and pad.active:
+        raise MpcB200Error("in-kernel dynamics need an exact (n_state, n_ctrl) kernel instance")
     L = _lib.lib()
     need_gains = want_gains or not do_rollout
     if not need_gains:
@@ -245,6 +253,9 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     params = Params(u_lo=float(s_lo), u_hi=float(s_hi),
                     delta_u=float(delta_u) if delta_u is not None else 0.0,
                     ls_decay=float(linesearch_decay))
+    if dyn is not None:
+        for i, v in enumerate(dyn[1]):
+            params.dyn[i] = float(v)
     fn = L.mpcb200_lqr_step_f32 if dtype == torch.float32 else L.mpcb200_lqr_step_f64
     with _on_device(dev):
         rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr(C_), ptr(c_), ptr(F_), ptr(f_), ptr(x0_),
@@ -479,6 +490,8 @@ def LQRStep(n_state,
     ``no_op_forward`` - differentiable w.r.t. ``x_init, C, c, F, f``.
     """
     from .solver import QuadCost, LinDx
+    from .dynamics import known_kind
+    _defer_host = getattr(_host_reads, "defer", None)
 
     class LQRStepFn(Function):
         @staticmethod
@@ -490,17 +503,23 @@ def LQRStep(n_state,
             assert current_x is not None and current_u is not None
             assert not (delta_u is not None and u_lower is None)   # reference :195
 
-            fused = (isinstance(true_cost, QuadCost) and isinstance(true_dynamics, LinDx)
-                     and _same_storage(true_cost.C, C) and _same_storage(true_cost.c, c)
+            quad_same = (isinstance(true_cost, QuadCost) and _same_storage(true_cost.C, C)
+                         and _same_storage(true_cost.c, c))
+            fused = (quad_same and isinstance(true_dynamics, LinDx)
                      and _same_storage(true_dynamics.F, F)
                      and (_same_storage(true_dynamics.f, f)
                           or (_is_empty(true_dynamics.f) and _is_empty(f))))
+            dyn = None
+            if quad_same and not fused and isinstance(true_dynamics, Module):
+                kind, kparams = known_kind(true_dynamics, n_state, n_ctrl, C)
+                if kind:                       # a known system: its step function runs inside the kernel
+                    dyn, fused = (kind, kparams), True
             if fused:
                 o = lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, current_x, current_u,
                                  u_lower=u_lower, u_upper=u_upper, u_zero_I=u_zero_I, delta_u=delta_u,
                                  linesearch_decay=linesearch_decay,
                                  max_linesearch_iter=max_linesearch_iter, do_rollout=True,
-                                 want_du_first=True)
+                                 want_du_first=True, dyn=dyn)
                 new_x, new_u = o["new_x"], o["new_u"]
                 costs, alphas = o["costs"], o["alphas"]
                 fdn = reference_full_du_norm(o["du_first"])
@@ -513,7 +532,13 @@ def LQRStep(n_state,
                     T, x_init.detach(), current_x.detach(), current_u.detach(), o["Ks"], o["ks"],
                     true_cost, true_dynamics, u_lower, u_upper, u_zero_I, delta_u,
                     linesearch_decay, max_linesearch_iter)
-            if u_lower is not None:
+            if u_lower is not None and _defer_host is not None:
+                # MPC's loop: no host read per step; the counters stay on the device and MPC reads them
+                # together with its own stop-test scalars (one sync per iteration)
+                _defer_host["n_qp"] = (1 + o["qp_iters"].max(dim=1).values).sum()
+                _defer_host["unconverged"] = (o["status"] & 1).any()
+                n_qp = float("nan")
+            elif u_lower is not None:
                 # reference: sum_t (1 + i_t) with one batched pnqp per step (:140)
                 n_qp = float((1 + o["qp_iters"].max(dim=1).values).sum().item())
                 if verbose >= 0 and bool((o["status"] & 1).any()):

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/mpcb200.h but not exported"
     assert set(syms) == set(_lib.EXPORTED_SYMBOLS)
-    assert L.mpcb200_version() == 1
+    assert L.mpcb200_version() == 2          # v2: dynamics_kind in mpcb200_dims, dyn[8] in mpcb200_params, mpcb200_dyn_*
     assert L.mpcb200_strerror(0) == b"ok"
     assert b"NULL" in L.mpcb200_strerror(1)
 

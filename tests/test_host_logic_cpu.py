@@ -115,7 +115,8 @@ def test_approximate_cost_recovers_a_quadratic():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (CPU arm = oracle port) must print one JSON line with the contract keys."""
+    """`bench.py --impl reference` (CPU arm: the unmodified reference when baseline/_ref travelled, else the
+    oracle port) must print one JSON line with the contract keys."""
     import json
     import os
     import subprocess
@@ -128,6 +129,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+    have_ref = os.path.exists(os.path.join(root, "baseline", "_ref", "mpc", "__init__.py"))
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert "workload" in line["config"] and "model" not in line["config"]
