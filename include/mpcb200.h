@@ -147,6 +147,32 @@ int mpcb200_lqr_grad_f64(const mpcb200_dims* dims,
                          void* workspace, void* stream);
 
 /*
+ * The whole KKT-adjoint backward in ONE call: replaces LQRStepFn.backward (reference mpc/lqr_step.py:312-407).
+ * Given the solution (new_x, new_u) of the forward solve and the upstream gradients dl_dx[T,B,n], dl_du[T,B,m]:
+ *   1. prep kernel: r = -[dl_dx; dl_du]; active set I = (|u* - u_lower| <= 1e-8) | (|u* - u_upper| <= 1e-8)
+ *      from the box (dims->bounds_kind / params->u_lo,u_hi / u_lower,u_upper), reference :316-326;
+ *   2. the masked LQR step from the zero trajectory (c = r, x_init = 0, u_zero_I = I, default line search),
+ *      i.e. the nested MPC(lqr_iter=1) of :328-340, with the step kernel;
+ *   3. costates and outer products (mpcb200_lqr_grad_*, :342-404).
+ * Outputs dx_init[B,n] dC[T,B,p,p] dc[T,B,p] dF[F_T,B,n,p] df[T-1,B,n] (df only if dims->has_f).
+ * workspace: device buffer of mpcb200_adjoint_workspace_bytes(dims, elem_size) bytes (scratch; contents
+ * undefined on return).  Only dims->{B,T,n,m,F_T,has_f,bounds_kind} and params->{u_lo,u_hi} are read.
+ */
+size_t mpcb200_adjoint_workspace_bytes(const mpcb200_dims* dims, int32_t elem_size);
+int mpcb200_lqr_adjoint_f32(const mpcb200_dims* dims, const mpcb200_params* params,
+                            const float* C, const float* c, const float* F,
+                            const float* new_x, const float* new_u, const float* dl_dx, const float* dl_du,
+                            const float* u_lower, const float* u_upper,
+                            float* dx_init, float* dC, float* dc, float* dF, float* df,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int mpcb200_lqr_adjoint_f64(const mpcb200_dims* dims, const mpcb200_params* params,
+                            const double* C, const double* c, const double* F,
+                            const double* new_x, const double* new_u, const double* dl_dx, const double* dl_du,
+                            const double* u_lower, const double* u_upper,
+                            double* dx_init, double* dC, double* dc, double* dF, double* df,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Nominal trajectory under LinDx dynamics: replaces util.get_traj for LinDx (reference
  * mpc/util.py:102-126, called once per iLQR iteration at mpc/mpc.py:251):
  *   x[0] = x_init;  x[t+1] = F[t] [x[t]; u[t]] + f[t]   (f may be NULL; dims->has_f)

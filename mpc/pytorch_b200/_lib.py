@@ -33,6 +33,7 @@ _lib = None
 EXPORTED_SYMBOLS = (
     "mpcb200_lqr_step_f32", "mpcb200_lqr_step_f64", "mpcb200_lqr_grad_f32", "mpcb200_lqr_grad_f64",
     "mpcb200_rollout_f32", "mpcb200_rollout_f64", "mpcb200_pnqp_f32", "mpcb200_pnqp_f64",
+    "mpcb200_lqr_adjoint_f32", "mpcb200_lqr_adjoint_f64", "mpcb200_adjoint_workspace_bytes",
     "mpcb200_dyn_rollout_f32", "mpcb200_dyn_rollout_f64", "mpcb200_dyn_linearize_f32", "mpcb200_dyn_linearize_f64",
     "mpcb200_supported", "mpcb200_supported_list", "mpcb200_launch_count",
     "mpcb200_step_smem_bytes", "mpcb200_step_prefers_workspace", "mpcb200_version", "mpcb200_strerror",
@@ -68,6 +69,12 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = [ctypes.c_int32, ctypes.c_int32] + [vp] * 5 + [ctypes.c_int32] + [vp] * 6
         fn.restype = ctypes.c_int
+    for name in ("mpcb200_lqr_adjoint_f32", "mpcb200_lqr_adjoint_f64"):
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.POINTER(Dims), ctypes.POINTER(Params)] + [vp] * 15 + [ctypes.c_size_t, vp]
+        fn.restype = ctypes.c_int
+    L.mpcb200_adjoint_workspace_bytes.argtypes = [ctypes.POINTER(Dims), ctypes.c_int32]
+    L.mpcb200_adjoint_workspace_bytes.restype = ctypes.c_size_t
     for name in ("mpcb200_dyn_rollout_f32", "mpcb200_dyn_rollout_f64"):
         fn = getattr(L, name)
         fn.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.c_int32] + [vp] * 4

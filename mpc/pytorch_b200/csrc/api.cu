@@ -167,6 +167,101 @@ static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, 
   if (rc == 0) g_launches.fetch_add(workspace != nullptr ? 2 : 1);
   return rc;
 }
+// ---------------------------------------------------------------------------------------------
+// KKT adjoint in one call (reference LQRStepFn.backward, mpc/lqr_step.py:312-407)
+// ---------------------------------------------------------------------------------------------
+struct AdjLayout {                    // workspace carve-up (byte offsets, every piece 256-byte aligned)
+  size_t negr, zeros, dx, du, costate, scal, mask, total;
+};
+static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+static AdjLayout adj_layout(int B, int T, int n, int m, size_t sz) {
+  AdjLayout l;
+  const size_t TB = (size_t)T * B;
+  size_t o = 0;
+  l.negr = o;    o += up256(TB * (n + m) * sz);
+  l.zeros = o;   o += up256((TB * (n + m) + (size_t)B * n) * sz);     // cur_x, cur_u, x_init of the nested solve
+  l.dx = o;      o += up256(TB * n * sz);
+  l.du = o;      o += up256(TB * m * sz);
+  l.costate = o; o += up256(2 * TB * n * sz);
+  l.scal = o;    o += up256((size_t)3 * B * sz);
+  l.mask = o;    o += up256(TB * m);
+  l.total = o;
+  return l;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+adjoint_prep_kernel(int B, int T, int n, int m, int bounds_kind, R s_lo, R s_hi, const R* __restrict__ dl_dx,
+                    const R* __restrict__ dl_du, const R* __restrict__ new_u, const R* __restrict__ u_lower,
+                    const R* __restrict__ u_upper, R* __restrict__ negr, unsigned char* __restrict__ mask) {
+  const size_t tb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tb >= (size_t)T * B) return;
+  const int p = n + m;
+  for (int i = 0; i < n; ++i) negr[tb * p + i] = -dl_dx[tb * n + i];
+  for (int q = 0; q < m; ++q) {
+    negr[tb * p + n + q] = -dl_du[tb * m + q];
+    unsigned char on = 0;
+    if (bounds_kind != 0) {                       // reference :325-326
+      const R u = new_u[tb * m + q];
+      const R lo = bounds_kind == 2 ? u_lower[tb * m + q] : s_lo;
+      const R hi = bounds_kind == 2 ? u_upper[tb * m + q] : s_hi;
+      on = (fabs(u - lo) <= R(1e-8)) || (fabs(u - hi) <= R(1e-8));
+    }
+    mask[tb * m + q] = on;
+  }
+}
+
+template <typename R>
+static int adjoint_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C, const R* c, const R* F,
+                        const R* new_x, const R* new_u, const R* dl_dx, const R* dl_du, const R* u_lower,
+                        const R* u_upper, R* dx_init, R* dC, R* dc, R* dF, R* df, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if (p == nullptr || C == nullptr || c == nullptr || new_x == nullptr || new_u == nullptr || dl_dx == nullptr ||
+      dl_du == nullptr || dx_init == nullptr || dC == nullptr || dc == nullptr || workspace == nullptr)
+    return MPCB200_ERR_NULL_POINTER;
+  if (d->T > 1 && (F == nullptr || dF == nullptr)) return MPCB200_ERR_NULL_POINTER;
+  if (d->bounds_kind < 0 || d->bounds_kind > 2) return MPCB200_ERR_BAD_DIMS;
+  if (d->bounds_kind == 2 && (u_lower == nullptr || u_upper == nullptr)) return MPCB200_ERR_NULL_POINTER;
+  if (d->has_f && df == nullptr) return MPCB200_ERR_NULL_POINTER;
+  const AdjLayout l = adj_layout(d->B, d->T, d->n, d->m, sizeof(R));
+  if (workspace_bytes < l.total || !aligned16(workspace)) return MPCB200_ERR_BAD_DIMS;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  R* negr = (R*)(ws + l.negr);
+  R* zeros = (R*)(ws + l.zeros);
+  R* dxs = (R*)(ws + l.dx);
+  R* dus = (R*)(ws + l.du);
+  R* scal = (R*)(ws + l.scal);
+  unsigned char* mask = (unsigned char*)(ws + l.mask);
+  const size_t TB = (size_t)d->T * d->B;
+  if (cudaMemsetAsync(zeros, 0, (TB * (d->n + d->m) + (size_t)d->B * d->n) * sizeof(R), st) != cudaSuccess)
+    return MPCB200_ERR_LAUNCH;
+  adjoint_prep_kernel<R><<<(unsigned)((TB + 255) / 256), 256, 0, st>>>(
+      d->B, d->T, d->n, d->m, d->bounds_kind, (R)p->u_lo, (R)p->u_hi, dl_dx, dl_du, new_u, u_lower, u_upper, negr, mask);
+  if (cudaGetLastError() != cudaSuccess) return MPCB200_ERR_LAUNCH;
+  g_launches.fetch_add(1);
+  // nested masked LQR step from the zero trajectory (reference :328-340: MPC(lqr_iter=1, u_zero_I=I) with its defaults)
+  mpcb200_dims ds = *d;
+  ds.has_f = 0; ds.bounds_kind = 0; ds.has_zero_mask = 1; ds.has_delta_u = 0;
+  ds.max_ls_iter = 10; ds.pnqp_max_iter = 20; ds.do_rollout = 1; ds.dynamics_kind = 0;
+  mpcb200_params ps;
+  std::memset(&ps, 0, sizeof(ps));
+  ps.ls_decay = 0.2;
+  R* zx = zeros;
+  R* zu = zeros + TB * d->n;
+  R* z0 = zu + TB * d->m;
+  rc = step_impl<R>(&ds, &ps, C, negr, F, (const R*)nullptr, z0, zx, zu, (const R*)nullptr, (const R*)nullptr, mask,
+                    dxs, dus, scal, scal + d->B, scal + 2 * d->B, (R*)nullptr, (int32_t*)nullptr,
+                    (uint8_t*)nullptr, (int32_t*)nullptr, (R*)nullptr, (R*)nullptr, stream);
+  if (rc == MPCB200_ERR_SMEM) return rc;     // long horizons: use the two-call path with Ks/ks buffers
+  if (rc) return rc;
+  mpcb200_dims dg = *d;
+  return grad_impl<R>(&dg, C, c, F, new_x, new_u, dxs, dus, dl_dx, dx_init, dC, dc, dF, d->has_f ? df : (R*)nullptr,
+                      ws + l.costate, stream);
+}
+
 template <typename R>
 static int rollout_impl(const mpcb200_dims* d, const R* F, const R* f, const R* x_init, const R* u, R* x,
                         void* stream) {
@@ -247,6 +342,27 @@ int mpcb200_lqr_grad_f64(const mpcb200_dims* dims, const double* C, const double
                          const double* dl_dx, double* dx_init, double* dC, double* dc, double* dF,
                          double* df, void* workspace, void* stream) {
   return grad_impl<double>(dims, C, c, F, new_x, new_u, dx, du, dl_dx, dx_init, dC, dc, dF, df, workspace, stream);
+}
+
+size_t mpcb200_adjoint_workspace_bytes(const mpcb200_dims* dims, int32_t elem_size) {
+  if (dims == nullptr || check_dims(dims) != 0 || (elem_size != 4 && elem_size != 8)) return 0;
+  return adj_layout(dims->B, dims->T, dims->n, dims->m, (size_t)elem_size).total;
+}
+int mpcb200_lqr_adjoint_f32(const mpcb200_dims* dims, const mpcb200_params* params, const float* C, const float* c,
+                            const float* F, const float* new_x, const float* new_u, const float* dl_dx,
+                            const float* dl_du, const float* u_lower, const float* u_upper, float* dx_init,
+                            float* dC, float* dc, float* dF, float* df, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return adjoint_impl<float>(dims, params, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper, dx_init, dC, dc,
+                             dF, df, workspace, workspace_bytes, stream);
+}
+int mpcb200_lqr_adjoint_f64(const mpcb200_dims* dims, const mpcb200_params* params, const double* C, const double* c,
+                            const double* F, const double* new_x, const double* new_u, const double* dl_dx,
+                            const double* dl_du, const double* u_lower, const double* u_upper, double* dx_init,
+                            double* dC, double* dc, double* dF, double* df, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return adjoint_impl<double>(dims, params, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper, dx_init, dC, dc,
+                              dF, df, workspace, workspace_bytes, stream);
 }
 
 int mpcb200_rollout_f32(const mpcb200_dims* dims, const float* F, const float* f, const float* x_init,

@@ -333,6 +333,83 @@ def lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dx, du, dl_dx, want_
     return dx_init, dC, dc, dF, df
 
 
+_ws_cache = threading.local()
+
+
+def _workspace(nbytes, dev):
+    """Scratch buffer for the one-call adjoint, reused per (thread, device, stream): the library call is
+    stream ordered, so consecutive backward passes on one stream can share it."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    store = getattr(_ws_cache, "store", None)
+    if store is None:
+        store = _ws_cache.store = {}
+    buf = store.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = store[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return buf
+
+
+def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper, want_df, f_T=None):
+    """LQRStepFn.backward in ONE library call (prep + nested masked step + costates + outer products);
+    returns (dx_init, dC, dc, dF, df|None), or None when this shape needs the general multi-call path
+    (zero-padded instance, horizon too long for the shared-memory gain store)."""
+    dtype, dev = C.dtype, C.device
+    n, m = n_state, n_ctrl
+    if _pick_instance(n, m) != (n, m) or _is_empty(F):
+        return None
+    B = C.shape[1]
+    p = n + m
+    _expect("C", C, (T, B, p, p), dev)
+    _expect("c", c, (T, B, p), dev)
+    _expect("F", F, (F.shape[0], B, n, p), dev)
+    for nm, t_, sh in (("new_x", new_x, (T, B, n)), ("new_u", new_u, (T, B, m)), ("dl_dx", dl_dx, (T, B, n)),
+                       ("dl_du", dl_du, (T, B, m))):
+        _expect(nm, t_, sh, dev)
+    F_T = F.shape[0]
+    kind, s_lo, s_hi, lo_t, hi_t = 0, 0.0, 0.0, None, None
+    if u_lower is not None:
+        if isinstance(u_lower, float) and isinstance(u_upper, float):
+            kind, s_lo, s_hi = 1, u_lower, u_upper
+        else:
+            kind = 2
+            lo_t = (torch.full((T, B, m), u_lower, dtype=dtype, device=dev) if isinstance(u_lower, float)
+                    else _dense(u_lower, dtype))
+            hi_t = (torch.full((T, B, m), u_upper, dtype=dtype, device=dev) if isinstance(u_upper, float)
+                    else _dense(u_upper, dtype))
+            _expect("u_lower", lo_t, (T, B, m), dev)
+            _expect("u_upper", hi_t, (T, B, m), dev)
+    dims = Dims(B=B, T=T, n=n, m=m, F_T=F_T, has_f=int(want_df), bounds_kind=kind, has_zero_mask=0,
+                has_delta_u=0, max_ls_iter=10, pnqp_max_iter=PNQP_MAX_ITER, do_rollout=1)
+    L = _lib.lib()
+    key = (n, m, T, C.element_size())
+    fits = _smem_fits_cache.get(key)
+    if fits is None:
+        fits = not L.mpcb200_step_prefers_workspace(ctypes.byref(dims), C.element_size())
+        _smem_fits_cache[key] = fits
+    if not fits:
+        return None
+    params = Params(u_lo=float(s_lo), u_hi=float(s_hi), delta_u=0.0, ls_decay=0.2)
+    C_, c_, F_ = _dense(C, dtype), _dense(c, dtype), _dense(F, dtype)
+    nx_, nu_, gx_, gu_ = _dense(new_x, dtype), _dense(new_u, dtype), _dense(dl_dx, dtype), _dense(dl_du, dtype)
+    dx_init = torch.empty(B, n, dtype=dtype, device=dev)
+    dC = torch.empty(T, B, p, p, dtype=dtype, device=dev)
+    dc = torch.empty(T, B, p, dtype=dtype, device=dev)
+    dF = torch.empty(F_T, B, n, p, dtype=dtype, device=dev)
+    f_T = T - 1 if f_T is None else f_T
+    df = torch.empty(f_T, B, n, dtype=dtype, device=dev) if want_df else None
+    if want_df and f_T == T:
+        df[T - 1].zero_()
+    nbytes = L.mpcb200_adjoint_workspace_bytes(ctypes.byref(dims), C.element_size())
+    ws = _workspace(nbytes, dev)
+    fn = L.mpcb200_lqr_adjoint_f32 if dtype == torch.float32 else L.mpcb200_lqr_adjoint_f64
+    with _on_device(dev):
+        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr(C_), ptr(c_), ptr(F_), ptr(nx_), ptr(nu_), ptr(gx_),
+                ptr(gu_), ptr(lo_t), ptr(hi_t), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), ptr(ws),
+                ctypes.c_size_t(nbytes), stream_handle(dev))
+    check(rc, "mpcb200_lqr_adjoint")
+    return dx_init, dC, dc, dF, df
+
+
 def rollout_raw(n_state, n_ctrl, T, x_init, u, F, f=None):
     """x = get_traj(T, u, x_init, LinDx(F, f)) in ONE kernel (reference mpc/util.py:102-126)."""
     dtype, dev = x_init.dtype, x_init.device
@@ -556,6 +633,14 @@ def LQRStep(n_state,
                 dl_dx = torch.zeros_like(new_x)
             if dl_du is None:
                 dl_du = torch.zeros_like(new_u)
+            want_df = not _is_empty(f)
+            fast = lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper,
+                                   want_df, f_T=f.shape[0] if want_df else None)
+            if fast is not None:                                # the whole backward in one library call
+                dx_init, dC, dc, dF, df = fast
+                if df is None:
+                    df = torch.zeros_like(f) if f is not None else None
+                return dx_init, dC, dc, dF, df
             r = torch.cat((dl_dx, dl_du), 2)                     # reference :316-320
             if u_lower is None:
                 I = None
