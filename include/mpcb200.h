@@ -62,6 +62,13 @@ typedef struct mpcb200_dims {
                              MPCB200_DYN_LINEAR = LinDx(F,f); MPCB200_DYN_CARTPOLE / _PENDULUM = the step
                              function of that system evaluated inside the kernel (params.dyn); F,f are
                              then its linearisation and are used by the Riccati sweep only (ABI v2)  */
+  int32_t reserved0;      /* 0 (keeps the 64-bit fields below naturally aligned)              */
+  /* Elements between consecutive TIME slices of C, c, F, f (ABI v2).  0: dense ([T,B,...] contiguous; what a
+   * zero-initialised struct means).  > 0: that many elements.  MPCB200_TIME_INVARIANT (-1): one [B,...] slice
+   * reused for every t (a torch stride of 0), which is what the reference's
+   * `C.unsqueeze(0).expand(T, ...)` hands over (mpc/mpc.py:205-226) and what an LTI system is; the slice is
+   * read from HBM / copied from the host once instead of T times.  The batch dimension stays dense. */
+  int64_t C_tstride, c_tstride, F_tstride, f_tstride;
 } mpcb200_dims;
 
 typedef struct mpcb200_params {
@@ -75,6 +82,7 @@ typedef struct mpcb200_params {
  * dyn[] = cartpole: gravity, masscart, masspole, length, force_mag, dt   (state x,dx,cos th,sin th,dth; n=5, m=1)
  *         pendulum: g, m, l, (unused), max_torque, dt                    (state cos th,sin th,dth; n=3, m=1) */
 enum { MPCB200_DYN_LINEAR = 0, MPCB200_DYN_CARTPOLE = 1, MPCB200_DYN_PENDULUM = 2 };
+#define MPCB200_TIME_INVARIANT (-1)
 
 /* Per-problem status bits written to `status[B]`. */
 #define MPCB200_ST_PNQP_UNCONVERGED 1u /* some time step hit pnqp_max_iter (reference prints a warning, pnqp.py:81) */

@@ -16,7 +16,9 @@ LIB_PATH = os.environ.get("MPCB200_LIB", os.path.join(_HERE, "libmpcb200.so"))  
 class Dims(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in (
         "B", "T", "n", "m", "F_T", "has_f", "bounds_kind", "has_zero_mask",
-        "has_delta_u", "max_ls_iter", "pnqp_max_iter", "do_rollout", "dynamics_kind")]
+        "has_delta_u", "max_ls_iter", "pnqp_max_iter", "do_rollout", "dynamics_kind", "reserved0")] + \
+        [(k, ctypes.c_int64) for k in ("C_tstride", "c_tstride", "F_tstride", "f_tstride")]
+
 
 
 class Params(ctypes.Structure):
@@ -126,6 +128,16 @@ def ptr(t):
         raise MpcB200Error("mpc.pytorch_b200 runs on CUDA tensors only (no CPU fallback)")
     if not t.is_contiguous():
         raise MpcB200Error("internal error: non-contiguous tensor reached the C ABI")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_view(t):
+    """Device pointer of the first element of a CUDA tensor whose layout the caller has already validated
+    (time-strided [T, B, ...] inputs: contiguous [B, ...] slices, any time stride)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MpcB200Error("mpc.pytorch_b200 runs on CUDA tensors only (no CPU fallback)")
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -70,6 +70,10 @@ static int max_smem_optin() {
   return cache[dev];
 }
 
+// element stride between time slices: 0 = dense (what a zero-initialised mpcb200_dims means), < 0 = time
+// invariant (stride 0), > 0 = that many elements
+static long long tstride(long long given, long long dense) { return given == 0 ? dense : (given < 0 ? 0 : given); }
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int check_dims(const mpcb200_dims* d) {
@@ -132,6 +136,12 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
   ok = ok && (x_init == nullptr || aligned16(x_init));
   ok = ok && ((size_t)d->B * d->m * sz) % 16 == 0 && ((size_t)d->B * d->n * sz) % 16 == 0;
   a.bulk_ok = ok ? 1 : 0;
+  a.C_ts = tstride(d->C_tstride, (long long)d->B * (d->n + d->m) * (d->n + d->m));
+  a.c_ts = tstride(d->c_tstride, (long long)d->B * (d->n + d->m));
+  a.F_ts = tstride(d->F_tstride, (long long)d->B * d->n * (d->n + d->m));
+  a.f_ts = tstride(d->f_tstride, (long long)d->B * d->n);
+  ok = ok && (a.C_ts * sz) % 16 == 0 && (a.c_ts * sz) % 16 == 0 && (a.F_ts * sz) % 16 == 0 && (a.f_ts * sz) % 16 == 0;
+  a.bulk_ok = ok ? 1 : 0;
   a.dyn_kind = d->dynamics_kind;
   if (a.dyn_kind != DYN_LINEAR) {
     const bool shape_ok = (a.dyn_kind == DYN_CARTPOLE && d->n == 5 && d->m == 1) ||
@@ -163,6 +173,9 @@ static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, 
   a.B = d->B; a.T = d->T; a.F_T = d->F_T; a.has_df = df != nullptr;
   a.C = C; a.c = c; a.F = F; a.new_x = new_x; a.new_u = new_u; a.dx = dx; a.du = du; a.dl_dx = dl_dx;
   a.dx_init = dx_init; a.dC = dC; a.dc = dc; a.dF = dF; a.df = df; a.workspace = workspace;
+  a.C_ts = tstride(d->C_tstride, (long long)d->B * (d->n + d->m) * (d->n + d->m));
+  a.c_ts = tstride(d->c_tstride, (long long)d->B * (d->n + d->m));
+  a.F_ts = tstride(d->F_tstride, (long long)d->B * d->n * (d->n + d->m));
   rc = (sizeof(R) == 4 ? e->grad32 : e->grad64)(a, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(workspace != nullptr ? 2 : 1);
   return rc;
@@ -246,6 +259,7 @@ static int adjoint_impl(const mpcb200_dims* d, const mpcb200_params* p, const R*
   mpcb200_dims ds = *d;
   ds.has_f = 0; ds.bounds_kind = 0; ds.has_zero_mask = 1; ds.has_delta_u = 0;
   ds.max_ls_iter = 10; ds.pnqp_max_iter = 20; ds.do_rollout = 1; ds.dynamics_kind = 0;
+  ds.c_tstride = 0; ds.f_tstride = 0;         // c of the nested solve is the dense -r; C and F keep the caller's strides
   mpcb200_params ps;
   std::memset(&ps, 0, sizeof(ps));
   ps.ls_decay = 0.2;
@@ -277,6 +291,8 @@ static int rollout_impl(const mpcb200_dims* d, const R* F, const R* f, const R* 
   std::memset(&a, 0, sizeof(a));
   a.B = d->B; a.T = d->T; a.has_f = d->has_f ? 1 : 0;
   a.F = F; a.f = f; a.x_init = x_init; a.u = u; a.x = x;
+  a.F_ts = tstride(d->F_tstride, (long long)d->B * d->n * (d->n + d->m));
+  a.f_ts = tstride(d->f_tstride, (long long)d->B * d->n);
   rc = (sizeof(R) == 4 ? e->roll32 : e->roll64)(a, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(1);
   return rc;

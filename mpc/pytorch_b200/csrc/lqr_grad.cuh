@@ -20,6 +20,7 @@ struct GradArgs {
   const void *C, *c, *F, *new_x, *new_u, *dx, *du, *dl_dx;
   void *dx_init, *dC, *dc, *dF, *df;
   void* workspace;   // optional: 2*T*B*n elements (lambda, dlambda) -> two-kernel path
+  long long C_ts, c_ts, F_ts;   // elements between consecutive time slices of C, c, F (0 = time invariant)
 };
 
 template <typename R, int N, int M>
@@ -122,17 +123,17 @@ lqr_grad_kernel(const GradArgs a) {
     // ---- costates (reference :355-385): row jr of C_t[:n,:], column jr of F_t[:, :n]
     R nl = R(0), ndl = R(0);
     {
-      const R* Crow = gC + (tb * P + jr) * P;
+      const R* Crow = gC + (size_t)t * a.C_ts + ((size_t)bb * P + jr) * P;
 #pragma unroll
       for (int i = 0; i < P; ++i) {
         const R cv = Crow[i];
         nl += cv * shfl(tj, base + i);
         ndl += cv * shfl(dj, base + i);
       }
-      nl += gc[tb * P + jr];
+      nl += gc[(size_t)t * a.c_ts + (size_t)bb * P + jr];
       ndl -= grx[tb * N + jr];
       if (t < T - 1) {
-        const R* Fc = gF + tb * N * P + jr;
+        const R* Fc = gF + (size_t)t * a.F_ts + (size_t)bb * N * P + jr;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           const R fv = Fc[k * P];
@@ -192,13 +193,13 @@ lqr_costate_kernel(const GradArgs a) {
     const size_t tb = (size_t)t * B + bb;
     o.tj = is_x ? __ldg(gx + tb * N + j) : __ldg(gu + tb * M + (j - N));
     o.dj = is_x ? __ldg(gdx + tb * N + j) : __ldg(gdu + tb * M + (j - N));
-    const R* Crow = gC + (tb * P + jr) * P;
+    const R* Crow = gC + (size_t)t * a.C_ts + ((size_t)bb * P + jr) * P;
 #pragma unroll
     for (int i = 0; i < P; ++i) o.crow[i] = __ldg(Crow + i);
-    o.cx = __ldg(gc + tb * P + jr);
+    o.cx = __ldg(gc + (size_t)t * a.c_ts + (size_t)bb * P + jr);
     o.rx = __ldg(grx + tb * N + jr);
     if (t < T - 1) {
-      const R* Fc = gF + tb * N * P + jr;
+      const R* Fc = gF + (size_t)t * a.F_ts + (size_t)bb * N * P + jr;
 #pragma unroll
       for (int k = 0; k < N; ++k) o.fcol[k] = __ldg(Fc + k * P);
     }

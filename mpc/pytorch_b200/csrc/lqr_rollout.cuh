@@ -13,6 +13,7 @@ struct RolloutArgs {
   int B, T, has_f;
   const void *F, *f, *x_init, *u;
   void* x;
+  long long F_ts, f_ts;   // elements between consecutive time slices of F, f (0 = time invariant)
 };
 
 template <typename R, int N, int M>
@@ -50,10 +51,10 @@ lqr_rollout_kernel(const RolloutArgs a) {
   };
   auto fetch = [&](int t, Tile& o) {
     const size_t tb = (size_t)t * B + bb;
-    const R* Fr = gF + (tb * N + r) * P;
+    const R* Fr = gF + (size_t)t * a.F_ts + ((size_t)bb * N + r) * P;
 #pragma unroll
     for (int i = 0; i < P; ++i) o.row[i] = __ldg(Fr + i);
-    o.fr = a.has_f ? __ldg(gf + tb * N + r) : R(0);
+    o.fr = a.has_f ? __ldg(gf + (size_t)t * a.f_ts + (size_t)bb * N + r) : R(0);
 #pragma unroll
     for (int q = 0; q < M; ++q) o.uu[q] = __ldg(gu + tb * M + q);
   };

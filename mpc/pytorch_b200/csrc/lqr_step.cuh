@@ -53,6 +53,7 @@ struct StepArgs {
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
   int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh)
+  long long C_ts, c_ts, F_ts, f_ts;   // elements between consecutive time slices of C, c, F, f (0 = time invariant)
   int dyn_kind;   // true dynamics of the rollout: DYN_LINEAR (F,f) or a known system evaluated in the kernel
   DynParams dp;
 };
@@ -259,6 +260,8 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
     mbar_wait(&empty[s], ph ^ 1u);
     R* st = (R*)(stage_base + (size_t)s * K::STAGE_BYTES);
     const size_t tb = (size_t)t * a.B + b0;
+    const size_t tC = (size_t)t * a.C_ts + (size_t)b0 * P * P, tF = (size_t)t * a.F_ts + (size_t)b0 * N * P;
+    const size_t tc = (size_t)t * a.c_ts + (size_t)b0 * P, tf_ = (size_t)t * a.f_ts + (size_t)b0 * N;
     const bool needF = t < T - 1;
     const bool needf = fwd && needF && a.has_f;
     if (a.has_mask) {
@@ -274,21 +277,21 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
         if (a.bounds_kind == 2) bytes += 2u * cnt * M * SZ;
         mbar_arrive_expect_tx(&full[s], bytes);
         if constexpr (K::CS == P * P) {
-          bulk_g2s(st + K::OFF_C, gC + tb * P * P, (uint32_t)cnt * P * P * SZ, &full[s]);
+          bulk_g2s(st + K::OFF_C, gC + tC, (uint32_t)cnt * P * P * SZ, &full[s]);
         } else {
           for (int q = 0; q < cnt; ++q)
-            bulk_g2s(st + K::OFF_C + q * K::CS, gC + (tb + q) * P * P, (uint32_t)P * P * SZ, &full[s]);
+            bulk_g2s(st + K::OFF_C + q * K::CS, gC + tC + (size_t)q * P * P, (uint32_t)P * P * SZ, &full[s]);
         }
         if (needF) {
           if constexpr (K::FS == N * P) {
-            bulk_g2s(st + K::OFF_F, gF + tb * N * P, (uint32_t)cnt * N * P * SZ, &full[s]);
+            bulk_g2s(st + K::OFF_F, gF + tF, (uint32_t)cnt * N * P * SZ, &full[s]);
           } else {
             for (int q = 0; q < cnt; ++q)
-              bulk_g2s(st + K::OFF_F + q * K::FS, gF + (tb + q) * N * P, (uint32_t)N * P * SZ, &full[s]);
+              bulk_g2s(st + K::OFF_F + q * K::FS, gF + tF + (size_t)q * N * P, (uint32_t)N * P * SZ, &full[s]);
           }
         }
-        bulk_g2s(st + K::OFF_c, gc + tb * P, (uint32_t)cnt * P * SZ, &full[s]);
-        if (needf) bulk_g2s(st + K::OFF_f, gf + tb * N, (uint32_t)cnt * N * SZ, &full[s]);
+        bulk_g2s(st + K::OFF_c, gc + tc, (uint32_t)cnt * P * SZ, &full[s]);
+        if (needf) bulk_g2s(st + K::OFF_f, gf + tf_, (uint32_t)cnt * N * SZ, &full[s]);
         bulk_g2s(st + K::OFF_x, gx + tb * N, (uint32_t)cnt * N * SZ, &full[s]);
         bulk_g2s(st + K::OFF_u, gu + tb * M, (uint32_t)cnt * M * SZ, &full[s]);
         if (a.bounds_kind == 2) {
@@ -300,11 +303,11 @@ MPCB_DEV void step_producer(const StepArgs& a, unsigned char* stage_base, uint64
       auto cp = [&](R* dst, const R* src, int nelem) {
         for (int i = lane; i < nelem; i += 32) dst[i] = __ldg(src + i);
       };
-      for (int q = 0; q < cnt; ++q) cp(st + K::OFF_C + q * K::CS, gC + (tb + q) * P * P, P * P);
+      for (int q = 0; q < cnt; ++q) cp(st + K::OFF_C + q * K::CS, gC + tC + (size_t)q * P * P, P * P);
       if (needF)
-        for (int q = 0; q < cnt; ++q) cp(st + K::OFF_F + q * K::FS, gF + (tb + q) * N * P, N * P);
-      cp(st + K::OFF_c, gc + tb * P, cnt * P);
-      if (needf) cp(st + K::OFF_f, gf + tb * N, cnt * N);
+        for (int q = 0; q < cnt; ++q) cp(st + K::OFF_F + q * K::FS, gF + tF + (size_t)q * N * P, N * P);
+      cp(st + K::OFF_c, gc + tc, cnt * P);
+      if (needf) cp(st + K::OFF_f, gf + tf_, cnt * N);
       cp(st + K::OFF_x, gx + tb * N, cnt * N);
       cp(st + K::OFF_u, gu + tb * M, cnt * M);
       if (a.bounds_kind == 2) {

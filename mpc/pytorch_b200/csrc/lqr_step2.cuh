@@ -103,7 +103,6 @@ struct Step2Cfg {
   static constexpr int L = P / 2;            // lanes per problem
   static constexpr int NXL = N / 2;          // x lanes (own two state columns each)
   static constexpr int PPW = L > 0 ? 32 / (L > 0 ? L : 1) : 1;   // problems per warp
-  static constexpr int S = MPCB2_STAGES;
   static constexpr int NW = MPCB2_NW;        // independent warps per CTA
   static constexpr int EA = 16 / (int)sizeof(R);
   static constexpr int SZ = (int)sizeof(R);
@@ -127,6 +126,11 @@ struct Step2Cfg {
   static constexpr int OFF_hi = OFF_lo + PPW * M;
   static constexpr int OFF_END = OFF_hi + PPW * M;
   static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
+  // ring depth: 4 stages for small tiles (a step is short, HBM latency spans several of them); 2 for big tiles
+  // (n >= 16: one step takes several microseconds, and shared memory is what keeps all warps of a 4096-problem
+  // batch resident in ONE wave - 1366 warps need <= 24 KB each)
+  static constexpr int S = STAGE_BYTES > 6144 ? 2 : MPCB2_STAGES;
+  static constexpr int MAX_REGS = STAGE_BYTES > 6144 ? 200 : 255;  // register budget that goes with it (10 warps / SM)
   // per-problem scratch (elements)
   static constexpr int NV = round_up(N, 4);             // row stride of V / K rows (16-byte aligned rows)
   static constexpr int VSTR = NV;
@@ -164,7 +168,7 @@ struct Step2Cfg {
 #endif
 
 template <typename R, int N, int M, int MODE, bool KSM>
-__global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32)
+__global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32) __maxnreg__((Step2Cfg<R, N, M>::MAX_REGS))
 lqr_step2_kernel(const StepArgs a) {
   using K = Step2Cfg<R, N, M>;
   constexpr int P = K::P, L = K::L, NXL = K::NXL, PPW = K::PPW, S = K::S, SZ = K::SZ, KT = K::KT, VSTR = K::VSTR, NV = K::NV;
@@ -257,8 +261,8 @@ lqr_step2_kernel(const StepArgs a) {
         "}" ::"r"(bar),                                                                    // 0
         "r"(by_base + (needF ? ucnt * (N * P) : 0u) + (needf ? ucnt * N : 0u)),             // 1
         "r"(dst), "r"(ucnt),                                                                 // 2 3
-        "l"(pC + tB * (P * P)), "l"(pF + tB * (N * P)), "l"(pc + tB * P), "l"(px + tB * N),  // 4 5 6 7
-        "l"(pu + tB * M), "l"(pf + tB * N), "l"(plo + tB * M), "l"(phi + tB * M),            // 8 9 10 11
+        "l"(pC + (size_t)t * a.C_ts * SZ), "l"(pF + (size_t)t * a.F_ts * SZ), "l"(pc + (size_t)t * a.c_ts * SZ), "l"(px + tB * N),  // 4 5 6 7
+        "l"(pu + tB * M), "l"(pf + (size_t)t * a.f_ts * SZ), "l"(plo + tB * M), "l"(phi + tB * M),     // 8 9 10 11
         "r"(needF), "r"(needf), "r"(has_tb),                                                 // 12 13 14
         "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),   // 15..21
         "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)              // 22..26

@@ -13,7 +13,7 @@ from torch.autograd import Function
 from torch.nn import Module
 
 from . import _lib
-from ._lib import Dims, Params, MpcB200Error, check, ptr, stream_handle
+from ._lib import Dims, Params, MpcB200Error, check, ptr, ptr_view, stream_handle
 
 PNQP_MAX_ITER = 20  # reference passes n_iter=20 (mpc/lqr_step.py:137)
 
@@ -47,6 +47,28 @@ def _expect(name, t, shape, dev):
         raise MpcB200Error(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
     if t.device != dev:
         raise MpcB200Error(f"{name}: expected a tensor on {dev}, got {t.device}")
+
+
+def _time_strided(t, dtype):
+    """(tensor, mpcb200_dims time-stride field) for a [T, B, ...] input WITHOUT materialising views whose
+    [B, ...] slices are contiguous: dense -> 0; stride-0 over time (`x.unsqueeze(0).expand(T, ...)`, an LTI
+    `F`, reference mpc/mpc.py:205-226) -> MPCB200_TIME_INVARIANT; any other 16-byte aligned time stride -> it.
+    Everything else (batch-expanded, transposed, ...) is copied to a dense tensor, as before."""
+    if t is None:
+        return None, 0
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.requires_grad:
+        t = t.detach()
+    if t.is_contiguous():
+        return t, 0
+    if t.dim() >= 2 and t.shape[0] > 0 and t[0].is_contiguous():
+        st0 = t.stride(0)
+        if st0 == 0:
+            return t, -1
+        if st0 > 0 and (st0 * t.element_size()) % 16 == 0:
+            return t, st0
+    return t.contiguous(), 0
 
 
 # ----------------------------------------------------------------------------------------------
@@ -181,9 +203,16 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     N, M = _pick_instance(n, m)
     pad = _Pad(n, m, N, M, dev)
 
-    C_, c_ = _dense(C, dtype), _dense(c, dtype)
-    F_ = _dense(F, dtype) if not _is_empty(F) else None
-    f_ = _dense(f, dtype) if not _is_empty(f) else None
+    ts = dict(C=0, c=0, F=0, f=0)
+    if pad.active:
+        C_, c_ = _dense(C, dtype), _dense(c, dtype)
+        F_ = _dense(F, dtype) if not _is_empty(F) else None
+        f_ = _dense(f, dtype) if not _is_empty(f) else None
+    else:       # honour time strides (time-invariant cost / LTI dynamics are read once, not T times)
+        C_, ts["C"] = _time_strided(C, dtype)
+        c_, ts["c"] = _time_strided(c, dtype)
+        F_, ts["F"] = _time_strided(F, dtype) if not _is_empty(F) else (None, 0)
+        f_, ts["f"] = _time_strided(f, dtype) if not _is_empty(f) else (None, 0)
     x0_ = _dense(x_init, dtype) if x_init is not None else None
     cx_, cu_ = _dense(cur_x, dtype), _dense(cur_u, dtype)
     F_T = F_.shape[0] if F_ is not None else T - 1
@@ -234,7 +263,8 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
     dims = Dims(B=B, T=T, n=N, m=M, F_T=F_T, has_f=int(f_ is not None), bounds_kind=bounds_kind,
                 has_zero_mask=int(zmask is not None), has_delta_u=int(delta_u is not None),
                 max_ls_iter=int(max_linesearch_iter), pnqp_max_iter=PNQP_MAX_ITER,
-                do_rollout=int(bool(do_rollout)), dynamics_kind=int(dyn[0]) if dyn is not None else 0)
+                do_rollout=int(bool(do_rollout)), dynamics_kind=int(dyn[0]) if dyn is not None else 0,
+                C_tstride=ts["C"], c_tstride=ts["c"], F_tstride=ts["F"], f_tstride=ts["f"])
     if dyn is not None and pad.active:
         raise MpcB200Error("in-kernel dynamics need an exact (n_state, n_ctrl) kernel instance")
     L = _lib.lib()
@@ -258,8 +288,8 @@ def lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, cur_x, cur_u,
             params.dyn[i] = float(v)
     fn = L.mpcb200_lqr_step_f32 if dtype == torch.float32 else L.mpcb200_lqr_step_f64
     with _on_device(dev):
-        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr(C_), ptr(c_), ptr(F_), ptr(f_), ptr(x0_),
-                ptr(cx_), ptr(cu_), ptr(lo_t), ptr(hi_t), ptr(zmask), ptr(new_x), ptr(new_u),
+        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr_view(C_), ptr_view(c_), ptr_view(F_), ptr_view(f_),
+                ptr(x0_), ptr(cx_), ptr(cu_), ptr(lo_t), ptr(hi_t), ptr(zmask), ptr(new_x), ptr(new_u),
                 ptr(costs), ptr(fdn), ptr(alphas), ptr(du_first), ptr(qp_iters), ptr(free_mask), ptr(status),
                 ptr(Ks), ptr(ks), stream_handle(dev))
     check(rc, "mpcb200_lqr_step")
@@ -389,7 +419,8 @@ def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_l
     if not fits:
         return None
     params = Params(u_lo=float(s_lo), u_hi=float(s_hi), delta_u=0.0, ls_decay=0.2)
-    C_, c_, F_ = _dense(C, dtype), _dense(c, dtype), _dense(F, dtype)
+    (C_, tsC), (c_, tsc), (F_, tsF) = _time_strided(C, dtype), _time_strided(c, dtype), _time_strided(F, dtype)
+    dims.C_tstride, dims.c_tstride, dims.F_tstride = tsC, tsc, tsF
     nx_, nu_, gx_, gu_ = _dense(new_x, dtype), _dense(new_u, dtype), _dense(dl_dx, dtype), _dense(dl_du, dtype)
     dx_init = torch.empty(B, n, dtype=dtype, device=dev)
     dC = torch.empty(T, B, p, p, dtype=dtype, device=dev)
@@ -403,7 +434,7 @@ def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_l
     ws = _workspace(nbytes, dev)
     fn = L.mpcb200_lqr_adjoint_f32 if dtype == torch.float32 else L.mpcb200_lqr_adjoint_f64
     with _on_device(dev):
-        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr(C_), ptr(c_), ptr(F_), ptr(nx_), ptr(nu_), ptr(gx_),
+        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr_view(C_), ptr_view(c_), ptr_view(F_), ptr(nx_), ptr(nu_), ptr(gx_),
                 ptr(gu_), ptr(lo_t), ptr(hi_t), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), ptr(ws),
                 ctypes.c_size_t(nbytes), stream_handle(dev))
     check(rc, "mpcb200_lqr_adjoint")
@@ -432,19 +463,25 @@ def rollout_raw(n_state, n_ctrl, T, x_init, u, F, f=None):
     N, M = _pick_instance(n, m)
     pad = _Pad(n, m, N, M, dev)
     x0_, u_ = _dense(x_init, dtype), _dense(u, dtype)
-    F_ = _dense(F, dtype) if not _is_empty(F) else None
-    f_ = _dense(f, dtype) if not _is_empty(f) else None
+    tsF = tsf = 0
+    if pad.active:
+        F_ = _dense(F, dtype) if not _is_empty(F) else None
+        f_ = _dense(f, dtype) if not _is_empty(f) else None
+    else:
+        F_, tsF = _time_strided(F, dtype) if not _is_empty(F) else (None, 0)
+        f_, tsf = _time_strided(f, dtype) if not _is_empty(f) else (None, 0)
     if pad.active:
         x0_, u_ = pad.vec_n(x0_), pad.vec_m(u_)
         F_ = pad.mat_np(F_) if F_ is not None else None
         f_ = pad.vec_n(f_) if f_ is not None else None
     x = torch.empty(T, B, N, dtype=dtype, device=dev)
     dims = Dims(B=B, T=T, n=N, m=M, F_T=F_.shape[0] if F_ is not None else T - 1, has_f=int(f_ is not None),
-                bounds_kind=0, has_zero_mask=0, has_delta_u=0, max_ls_iter=1, pnqp_max_iter=1, do_rollout=1)
+                bounds_kind=0, has_zero_mask=0, has_delta_u=0, max_ls_iter=1, pnqp_max_iter=1, do_rollout=1,
+                F_tstride=tsF, f_tstride=tsf)
     L = _lib.lib()
     fn = L.mpcb200_rollout_f32 if dtype == torch.float32 else L.mpcb200_rollout_f64
     with _on_device(dev):
-        rc = fn(ctypes.byref(dims), ptr(F_), ptr(f_), ptr(x0_), ptr(u_), ptr(x), stream_handle(dev))
+        rc = fn(ctypes.byref(dims), ptr_view(F_), ptr_view(f_), ptr(x0_), ptr(u_), ptr(x), stream_handle(dev))
     check(rc, "mpcb200_rollout")
     return x[..., :n] if pad.active else x
 
@@ -540,6 +577,110 @@ def _same_storage(a, b):
 
 
 # ----------------------------------------------------------------------------------------------
+# the autograd node
+# ----------------------------------------------------------------------------------------------
+class LQRStepFn(Function):
+    """The autograd node behind LQRStep(...).  ONE class for every call (the reference builds a new Function
+    class per call, mpc/lqr_step.py:275; the Python class creation alone costs more than the kernels at
+    config 3): the closure arguments travel as the first, non-tensor argument `o`."""
+    @staticmethod
+    def forward(ctx, o, x_init, C, c, F, f=None):
+        from .solver import QuadCost, LinDx
+        from .dynamics import known_kind
+        ctx.o = o
+        if o.no_op_forward:                                   # reference :278-282
+            ctx.save_for_backward(x_init, C, c, F, f, o.current_x, o.current_u)
+            return o.current_x, o.current_u
+        assert o.delta_space                                  # reference :284,298
+        assert o.current_x is not None and o.current_u is not None
+        assert not (o.delta_u is not None and o.u_lower is None)   # reference :195
+
+        quad_same = (isinstance(o.true_cost, QuadCost) and _same_storage(o.true_cost.C, C)
+                     and _same_storage(o.true_cost.c, c))
+        fused = (quad_same and isinstance(o.true_dynamics, LinDx)
+                 and _same_storage(o.true_dynamics.F, F)
+                 and (_same_storage(o.true_dynamics.f, f)
+                      or (_is_empty(o.true_dynamics.f) and _is_empty(f))))
+        dyn = None
+        if quad_same and not fused and isinstance(o.true_dynamics, Module):
+            kind, kparams = known_kind(o.true_dynamics, o.n_state, o.n_ctrl, C)
+            if kind:                       # a known system: its step function runs inside the kernel
+                dyn, fused = (kind, kparams), True
+        if fused:
+            res = lqr_step_raw(o.n_state, o.n_ctrl, o.T, x_init, C, c, F, f, o.current_x, o.current_u,
+                               u_lower=o.u_lower, u_upper=o.u_upper, u_zero_I=o.u_zero_I, delta_u=o.delta_u,
+                               linesearch_decay=o.linesearch_decay,
+                               max_linesearch_iter=o.max_linesearch_iter, do_rollout=True,
+                               want_du_first=True, dyn=dyn)
+            new_x, new_u = res["new_x"], res["new_u"]
+            costs, alphas = res["costs"], res["alphas"]
+            fdn = reference_full_du_norm(res["du_first"])
+        else:
+            assert o.true_cost is not None and o.true_dynamics is not None
+            res = lqr_step_raw(o.n_state, o.n_ctrl, o.T, x_init, C, c, F, f, o.current_x, o.current_u,
+                               u_lower=o.u_lower, u_upper=o.u_upper, u_zero_I=o.u_zero_I, delta_u=o.delta_u,
+                               do_rollout=False)
+            new_x, new_u, costs, fdn, alphas = rollout_split(
+                o.T, x_init.detach(), o.current_x.detach(), o.current_u.detach(), res["Ks"], res["ks"],
+                o.true_cost, o.true_dynamics, o.u_lower, o.u_upper, o.u_zero_I, o.delta_u,
+                o.linesearch_decay, o.max_linesearch_iter)
+        if o.u_lower is not None and o._defer_host is not None:
+            # MPC's loop: no host read per step; the counters stay on the device and MPC reads them
+            # together with its own stop-test scalars (one sync per iteration)
+            o._defer_host["n_qp"] = (1 + res["qp_iters"].max(dim=1).values).sum()
+            o._defer_host["unconverged"] = (res["status"] & 1).any()
+            n_qp = float("nan")
+        elif o.u_lower is not None:
+            # reference: sum_t (1 + i_t) with one batched pnqp per step (:140)
+            n_qp = float((1 + res["qp_iters"].max(dim=1).values).sum().item())
+            if o.verbose >= 0 and bool((res["status"] & 1).any()):
+                print("[WARNING] pnqp warning: Did not converge")   # reference pnqp.py:81
+        else:
+            n_qp = 0.0
+        ctx.save_for_backward(x_init, C, c, F, f, new_x, new_u)
+        return new_x, new_u, torch.Tensor([n_qp]), costs, fdn, alphas.mean()
+
+    @staticmethod
+    def backward(ctx, dl_dx, dl_du, temp=None, temp2=None, temp3=None, temp4=None):
+        o = ctx.o
+        x_init, C, c, F, f, new_x, new_u = ctx.saved_tensors
+        B = C.size(1)
+        if dl_dx is None:
+            dl_dx = torch.zeros_like(new_x)
+        if dl_du is None:
+            dl_du = torch.zeros_like(new_u)
+        want_df = not _is_empty(f)
+        fast = lqr_adjoint_raw(o.n_state, o.n_ctrl, o.T, C, c, F, new_x, new_u, dl_dx, dl_du, o.u_lower, o.u_upper,
+                               want_df, f_T=f.shape[0] if want_df else None)
+        if fast is not None:                                # the whole backward in one library call
+            dx_init, dC, dc, dF, df = fast
+            if df is None:
+                df = torch.zeros_like(f) if f is not None else None
+            return None, dx_init, dC, dc, dF, df
+        r = torch.cat((dl_dx, dl_du), 2)                     # reference :316-320
+        if o.u_lower is None:
+            I = None
+        else:                                               # reference :325-326
+            I = (torch.abs(new_u - o.u_lower) <= 1e-8) | (torch.abs(new_u - o.u_upper) <= 1e-8)
+        zx = torch.zeros(o.T, B, o.n_state, dtype=C.dtype, device=C.device)
+        zu = torch.zeros(o.T, B, o.n_ctrl, dtype=C.dtype, device=C.device)
+        # nested MPC(lqr_iter=1, u_zero_I=I)(0, QuadCost(C,-r), LinDx(F,None)) (reference :328-340):
+        # one masked LQR step from the zero trajectory with the reference's default line search.
+        res = lqr_step_raw(o.n_state, o.n_ctrl, o.T, torch.zeros_like(x_init), C, -r, F, None, zx, zu,
+                           u_zero_I=I, linesearch_decay=0.2, max_linesearch_iter=10,
+                           do_rollout=True, want_stats=False)
+        want_df = not _is_empty(f)
+        dx_init, dC, dc, dF, df = lqr_grad_raw(o.n_state, o.n_ctrl, o.T, C, c, F, new_x, new_u,
+                                               res["new_x"], res["new_u"], dl_dx, want_df,
+                                               f_T=f.shape[0] if want_df else None)
+        if dF is None:
+            dF = torch.zeros_like(F)
+        if df is None:                                       # reference :402 (empty tensor)
+            df = torch.zeros_like(f) if f is not None else None
+        return None, dx_init, dC, dc, dF, df
+
+
+# ----------------------------------------------------------------------------------------------
 # the factory (reference mpc/lqr_step.py:22-38)
 # ----------------------------------------------------------------------------------------------
 def LQRStep(n_state,
@@ -566,101 +707,14 @@ def LQRStep(n_state,
     full_du_norm[B], mean_alphas (0-d))`` - or ``(current_x, current_u)`` when
     ``no_op_forward`` - differentiable w.r.t. ``x_init, C, c, F, f``.
     """
-    from .solver import QuadCost, LinDx
-    from .dynamics import known_kind
-    _defer_host = getattr(_host_reads, "defer", None)
+    from types import SimpleNamespace
+    o = SimpleNamespace(n_state=n_state, n_ctrl=n_ctrl, T=T, u_lower=u_lower, u_upper=u_upper, u_zero_I=u_zero_I,
+                        delta_u=delta_u, linesearch_decay=linesearch_decay, max_linesearch_iter=max_linesearch_iter,
+                        true_cost=true_cost, true_dynamics=true_dynamics, delta_space=delta_space,
+                        current_x=current_x, current_u=current_u, verbose=verbose, back_eps=back_eps,
+                        no_op_forward=no_op_forward, _defer_host=getattr(_host_reads, "defer", None))
 
-    class LQRStepFn(Function):
-        @staticmethod
-        def forward(ctx, x_init, C, c, F, f=None):
-            if no_op_forward:                                   # reference :278-282
-                ctx.save_for_backward(x_init, C, c, F, f, current_x, current_u)
-                return current_x, current_u
-            assert delta_space                                  # reference :284,298
-            assert current_x is not None and current_u is not None
-            assert not (delta_u is not None and u_lower is None)   # reference :195
+    def apply(x_init, C, c, F, f=None):
+        return LQRStepFn.apply(o, x_init, C, c, F, f)
+    return apply
 
-            quad_same = (isinstance(true_cost, QuadCost) and _same_storage(true_cost.C, C)
-                         and _same_storage(true_cost.c, c))
-            fused = (quad_same and isinstance(true_dynamics, LinDx)
-                     and _same_storage(true_dynamics.F, F)
-                     and (_same_storage(true_dynamics.f, f)
-                          or (_is_empty(true_dynamics.f) and _is_empty(f))))
-            dyn = None
-            if quad_same and not fused and isinstance(true_dynamics, Module):
-                kind, kparams = known_kind(true_dynamics, n_state, n_ctrl, C)
-                if kind:                       # a known system: its step function runs inside the kernel
-                    dyn, fused = (kind, kparams), True
-            if fused:
-                o = lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, current_x, current_u,
-                                 u_lower=u_lower, u_upper=u_upper, u_zero_I=u_zero_I, delta_u=delta_u,
-                                 linesearch_decay=linesearch_decay,
-                                 max_linesearch_iter=max_linesearch_iter, do_rollout=True,
-                                 want_du_first=True, dyn=dyn)
-                new_x, new_u = o["new_x"], o["new_u"]
-                costs, alphas = o["costs"], o["alphas"]
-                fdn = reference_full_du_norm(o["du_first"])
-            else:
-                assert true_cost is not None and true_dynamics is not None
-                o = lqr_step_raw(n_state, n_ctrl, T, x_init, C, c, F, f, current_x, current_u,
-                                 u_lower=u_lower, u_upper=u_upper, u_zero_I=u_zero_I, delta_u=delta_u,
-                                 do_rollout=False)
-                new_x, new_u, costs, fdn, alphas = rollout_split(
-                    T, x_init.detach(), current_x.detach(), current_u.detach(), o["Ks"], o["ks"],
-                    true_cost, true_dynamics, u_lower, u_upper, u_zero_I, delta_u,
-                    linesearch_decay, max_linesearch_iter)
-            if u_lower is not None and _defer_host is not None:
-                # MPC's loop: no host read per step; the counters stay on the device and MPC reads them
-                # together with its own stop-test scalars (one sync per iteration)
-                _defer_host["n_qp"] = (1 + o["qp_iters"].max(dim=1).values).sum()
-                _defer_host["unconverged"] = (o["status"] & 1).any()
-                n_qp = float("nan")
-            elif u_lower is not None:
-                # reference: sum_t (1 + i_t) with one batched pnqp per step (:140)
-                n_qp = float((1 + o["qp_iters"].max(dim=1).values).sum().item())
-                if verbose >= 0 and bool((o["status"] & 1).any()):
-                    print("[WARNING] pnqp warning: Did not converge")   # reference pnqp.py:81
-            else:
-                n_qp = 0.0
-            ctx.save_for_backward(x_init, C, c, F, f, new_x, new_u)
-            return new_x, new_u, torch.Tensor([n_qp]), costs, fdn, alphas.mean()
-
-        @staticmethod
-        def backward(ctx, dl_dx, dl_du, temp=None, temp2=None, temp3=None, temp4=None):
-            x_init, C, c, F, f, new_x, new_u = ctx.saved_tensors
-            B = C.size(1)
-            if dl_dx is None:
-                dl_dx = torch.zeros_like(new_x)
-            if dl_du is None:
-                dl_du = torch.zeros_like(new_u)
-            want_df = not _is_empty(f)
-            fast = lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper,
-                                   want_df, f_T=f.shape[0] if want_df else None)
-            if fast is not None:                                # the whole backward in one library call
-                dx_init, dC, dc, dF, df = fast
-                if df is None:
-                    df = torch.zeros_like(f) if f is not None else None
-                return dx_init, dC, dc, dF, df
-            r = torch.cat((dl_dx, dl_du), 2)                     # reference :316-320
-            if u_lower is None:
-                I = None
-            else:                                               # reference :325-326
-                I = (torch.abs(new_u - u_lower) <= 1e-8) | (torch.abs(new_u - u_upper) <= 1e-8)
-            zx = torch.zeros(T, B, n_state, dtype=C.dtype, device=C.device)
-            zu = torch.zeros(T, B, n_ctrl, dtype=C.dtype, device=C.device)
-            # nested MPC(lqr_iter=1, u_zero_I=I)(0, QuadCost(C,-r), LinDx(F,None)) (reference :328-340):
-            # one masked LQR step from the zero trajectory with the reference's default line search.
-            o = lqr_step_raw(n_state, n_ctrl, T, torch.zeros_like(x_init), C, -r, F, None, zx, zu,
-                             u_zero_I=I, linesearch_decay=0.2, max_linesearch_iter=10,
-                             do_rollout=True, want_stats=False)
-            want_df = not _is_empty(f)
-            dx_init, dC, dc, dF, df = lqr_grad_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u,
-                                                   o["new_x"], o["new_u"], dl_dx, want_df,
-                                                   f_T=f.shape[0] if want_df else None)
-            if dF is None:
-                dF = torch.zeros_like(F)
-            if df is None:                                       # reference :402 (empty tensor)
-                df = torch.zeros_like(f) if f is not None else None
-            return dx_init, dC, dc, dF, df
-
-    return LQRStepFn.apply
