@@ -56,18 +56,18 @@ static std::atomic<uint64_t> g_launches{0};
 
 // per-device opt-in shared memory limit (cached for up to 64 devices)
 static int max_smem_optin() {
-  static int cache[64];
+  static std::atomic<int> cache[64];         // written once per device with the same value: safe from any thread
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   if (dev < 0 || dev >= 64) return -1;
-  if (cache[dev] == 0) {
+  if (cache[dev].load(std::memory_order_acquire) == 0) {
     int v = 0, major = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
     if (major != 10) return -1;   // sm_100a cubin only
-    cache[dev] = v;
+    cache[dev].store(v, std::memory_order_release);
   }
-  return cache[dev];
+  return cache[dev].load(std::memory_order_acquire);
 }
 
 // element stride between time slices: 0 = dense (what a zero-initialised mpcb200_dims means), < 0 = time

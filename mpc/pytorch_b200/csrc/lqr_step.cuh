@@ -29,6 +29,7 @@
 // compile-time knobs (two columns per lane, V in registers, padded tiles, mma.sync products, phase timers)
 // are described with their measurements in DESIGN.md section 7; their code was removed.
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include "common.cuh"
 #include "dynamics.cuh"
@@ -883,14 +884,16 @@ int launch_step_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stre
     if (a.do_rollout && !have_ws) return 4;
   }
   auto kern = lqr_step_kernel<R, N, M, MODE>;
-  static int configured[64] = {0};           // per device: the opt-in shared-memory attribute is per context
+  // per device: the opt-in shared-memory attribute is per context.  Atomic flags: concurrent callers (one host
+  // thread per GPU is the expected pattern) may both set the attribute - idempotent - but never read a torn value.
+  static std::atomic<int> configured[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 6;
-  if (configured[dev] < (int)smem) {
+  if (configured[dev].load(std::memory_order_acquire) < (int)smem) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) !=
         cudaSuccess)
       return 5;
-    configured[dev] = max_smem_optin;
+    configured[dev].store(max_smem_optin, std::memory_order_release);
   }
   const int grid = (a.B + K::W - 1) / K::W;
   kern<<<grid, K::THREADS, smem, stream>>>(a);

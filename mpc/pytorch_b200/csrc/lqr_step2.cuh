@@ -126,11 +126,11 @@ struct Step2Cfg {
   static constexpr int OFF_hi = OFF_lo + PPW * M;
   static constexpr int OFF_END = OFF_hi + PPW * M;
   static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
-  // ring depth: 4 stages for small tiles (a step is short, HBM latency spans several of them); 2 for big tiles
-  // (n >= 16: one step takes several microseconds, and shared memory is what keeps all warps of a 4096-problem
-  // batch resident in ONE wave - 1366 warps need <= 24 KB each)
-  static constexpr int S = STAGE_BYTES > 6144 ? 2 : MPCB2_STAGES;
-  static constexpr int MAX_REGS = STAGE_BYTES > 6144 ? 200 : 255;  // register budget that goes with it (10 warps / SM)
+  // ring depth.  Measured for n=16, m=4 (9.3 KB tiles): 2 stages + a 200-register cap (9 warps / SM instead of 5)
+  // is SLOWER (688 vs 449 us at B=4096, 1953 vs 1463 us at B=16384): the spills and the single tile of
+  // prefetch cost more than the extra resident warps bring.
+  static constexpr int S = MPCB2_STAGES;
+  static constexpr int MAX_REGS = 255;
   // per-problem scratch (elements)
   static constexpr int NV = round_up(N, 4);             // row stride of V / K rows (16-byte aligned rows)
   static constexpr int VSTR = NV;

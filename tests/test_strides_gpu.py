@@ -29,9 +29,9 @@ def test_time_invariant_and_strided_inputs_equal_dense(n, m, B, T, bounds):
     a = lqr_step_raw(n, m, T, x0, C_ti, c_str, F_lti, f, x, u, **kw)
     b = lqr_step_raw(n, m, T, x0, C_ti.contiguous(), c_str.contiguous(), F_lti.contiguous(), f, x, u, **kw)
     torch.cuda.synchronize()
-    for k in ("new_x", "new_u", "costs", "alphas", "full_du_norm"):
+    for k in ("new_x", "new_u", "costs", "alphas", "full_du_norm", "status", "free_mask"):
         assert torch.equal(a[k], b[k]), k
-    assert int(a["status"].max()) == 0
+    assert int((a["status"] & ~1).max()) == 0        # (bit 0: an fp32 pnqp instance at the iteration cap, same in both)
 
 
 def test_gradient_of_an_lti_system_sums_over_time():

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-config measurements (BASELINE.json configs 1-5) of the step kernel, device resident, + the
-adjoint path and the cartpole MPC loop.  Prints a markdown table (-> profiles/RESULTS_r01.md)."""
+adjoint path and the cartpole MPC loop.  Prints a markdown table (-> profiles/r02_results_per_config.md)."""
 import ctypes, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -57,20 +57,33 @@ for name, B, T, n, m, bounds, us, msps, gbs, bps in rows:
     print(f"| {name} | {B},{T},{n},{m} | {bounds} | {us:.1f} | {msps:.2f} | {gbs:.0f} | {gbs / PEAK:.3f} | {bps} |")
 print("\n(time/launch includes the Python/ctypes launch path of `lqr_step_raw`; small configs are launch bound.)")
 
-# cartpole MPC (config 2 recipe), full iLQR
+# cartpole MPC (config 2 recipe), full iLQR: known system in the kernels vs the same physics as an opaque Module
 from mpc import mpc
-from tests.cartpole import Cartpole, initial_states
+from mpc.env_dx.cartpole import CartpoleDx
+from tests.cartpole import initial_states
 B, T = 128, 25
+dx = CartpoleDx()
+
+
+class Opaque(torch.nn.Module):
+    def forward(self, x, u):
+        return dx(x, u)
+
+
 x0 = initial_states(B, 0).to(dev)
-q, p = Cartpole.objective()
+q, p = dx.get_true_obj()
 Q = torch.diag(q).repeat(T, B, 1, 1).to(dev)
 pp = p.repeat(T, B, 1).to(dev)
-for gm in (mpc.GradMethods.AUTO_DIFF,):
+print()
+for name, dyn in (("known system: rollout, Jacobians and line search inside kernels", dx),
+                  ("opaque nn.Module: autograd linearisation + torch rollout (round-1 path)", Opaque())):
     ctrl = mpc.MPC(5, 1, T, u_lower=-100.0, u_upper=100.0, lqr_iter=50, verbose=-1, exit_unconverged=False,
-                   detach_unconverged=False, linesearch_decay=0.5, max_linesearch_iter=2, grad_method=gm, eps=1e-2)
-    ctrl(x0, mpc.QuadCost(Q, pp), Cartpole())
+                   detach_unconverged=False, linesearch_decay=0.5, max_linesearch_iter=2,
+                   grad_method=mpc.GradMethods.AUTO_DIFF, eps=1e-2)
+    ctrl(x0, mpc.QuadCost(Q, pp), dyn)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    ctrl(x0, mpc.QuadCost(Q, pp), Cartpole())
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(f"\ncartpole MPC.forward (B=128,T=25, <=50 iLQR iterations, {gm.name}): {dt:.3f} s -> {B / dt:.0f} MPC-solves/s "
-          f"(reference CPU, SURVEY section 6: 5.85 s, 22 MPC-solves/s)")
+    for _ in range(3):
+        ctrl(x0, mpc.QuadCost(Q, pp), dyn)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+    print(f"cartpole MPC.forward (config 2: B=128, T=25, <=50 iLQR iterations, AUTO_DIFF), {name}: {dt * 1e3:.1f} ms -> "
+          f"{B / dt:.0f} MPC-solves/s  (reference CPU, SURVEY section 6: 5.85 s, 22 MPC-solves/s)")
