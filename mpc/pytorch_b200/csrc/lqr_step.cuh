@@ -53,7 +53,7 @@ struct StepArgs {
   void *Ks, *ks;
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
-  int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh)
+  int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh), 3 pair + producer warp
   long long C_ts, c_ts, F_ts, f_ts;   // elements between consecutive time slices of C, c, F, f (0 = time invariant)
   int dyn_kind;   // true dynamics of the rollout: DYN_LINEAR (F,f) or a known system evaluated in the kernel
   DynParams dp;

@@ -103,7 +103,8 @@ struct Step2Cfg {
   static constexpr int L = P / 2;            // lanes per problem
   static constexpr int NXL = N / 2;          // x lanes (own two state columns each)
   static constexpr int PPW = L > 0 ? 32 / (L > 0 ? L : 1) : 1;   // problems per warp
-  static constexpr int NW = MPCB2_NW;        // independent warps per CTA
+  static constexpr int NW = MPCB2_NW;        // independent (self-feeding) warps per CTA
+  static constexpr int NWC_PROD = 2;         // consumer warps per CTA in the producer variant (+ 1 producer warp)
   static constexpr int EA = 16 / (int)sizeof(R);
   static constexpr int SZ = (int)sizeof(R);
   // shapes this mapping supports: even n, m; per-warp spans of C and F 16-byte multiples (always true for even
@@ -115,6 +116,7 @@ struct Step2Cfg {
   // 1.5-1.8x at n=16, m=4) and for narrow problems (n+m <= 6, where 10+ problems share a warp); in between
   // (n=8, m=2: 39 vs 37 us at config 3) the step is latency bound either way and the generic kernel stays.
   static constexpr bool PAIR_DEFAULT = OK && (P >= 18 || P <= 6 || (N == 8 && M == 4));
+  static constexpr bool PRODUCER_DEFAULT = false;   // a.impl == 3 selects the producer-warp variant
   // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + PPW * P * P;
@@ -167,23 +169,141 @@ struct Step2Cfg {
 #define TICK2(arr, i)
 #endif
 
-template <typename R, int N, int M, int MODE, bool KSM>
-__global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32) __maxnreg__((Step2Cfg<R, N, M>::MAX_REGS))
+// One warp's tile stream: where its spans start in global memory and where its ring lives in shared memory.
+struct TileSrc {
+  const char *pC, *pF, *pc, *px, *pu, *pf, *plo, *phi;
+  uint32_t ucnt;      // bytes per element-of-a-problem over the warp's problems (cnt * sizeof(R))
+  uint32_t stage0;    // shared address of stage 0
+  uint32_t bar0;      // shared address of full[0]
+};
+
+// Start the bulk copies of tile (t, fwd) into ring stage `stage` of the warp described by `ts`.  Branch free:
+// one elected lane of the CALLING warp arrives on the stage's mbarrier with the byte count and issues up to
+// eight copies (predicated PTX; UBLKCP executes once per warp).
+template <typename R, int N, int M>
+MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t, bool fwd, int has_tb) {
+  using K = Step2Cfg<R, N, M>;
+  constexpr int P = K::P, SZ = K::SZ;
+  const uint32_t dst = ts.stage0 + (uint32_t)stage * K::STAGE_BYTES;
+  const uint32_t bar = ts.bar0 + (uint32_t)stage * 8u;
+  const int needF = t < a.T - 1 ? 1 : 0;
+  const int needf = (fwd && needF && a.has_f) ? 1 : 0;
+  const size_t tB = (size_t)t * a.B * SZ;
+  const uint32_t total = ts.ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0)) + (needF ? ts.ucnt * (N * P) : 0u) +
+                         (needf ? ts.ucnt * N : 0u);
+  asm volatile(
+      "{\n\t.reg .pred P, PF, Pf, PB;\n\t.reg .b32 d, n;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "setp.ne.and.b32 PF, %12, 0, P;\n\t"
+      "setp.ne.and.b32 Pf, %13, 0, P;\n\t"
+      "setp.ne.and.b32 PB, %14, 0, P;\n\t"
+      "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "mul.lo.u32 n, %3, %15;\n\t"
+      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
+      "mul.lo.u32 n, %3, %16;\n\tadd.u32 d, %2, %17;\n\t"
+      "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%5], n, [%0];\n\t"
+      "mul.lo.u32 n, %3, %18;\n\tadd.u32 d, %2, %19;\n\t"
+      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%6], n, [%0];\n\t"
+      "mul.lo.u32 n, %3, %20;\n\tadd.u32 d, %2, %21;\n\t"
+      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%7], n, [%0];\n\t"
+      "add.u32 d, %2, %23;\n\t"
+      "@Pf cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%9], n, [%0];\n\t"
+      "mul.lo.u32 n, %3, %22;\n\tadd.u32 d, %2, %24;\n\t"
+      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%8], n, [%0];\n\t"
+      "add.u32 d, %2, %25;\n\t"
+      "@PB cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%10], n, [%0];\n\t"
+      "add.u32 d, %2, %26;\n\t"
+      "@PB cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%11], n, [%0];\n\t"
+      "}" ::"r"(bar), "r"(total), "r"(dst), "r"(ts.ucnt),                                                      // 0..3
+      "l"(ts.pC + (size_t)t * a.C_ts * SZ), "l"(ts.pF + (size_t)t * a.F_ts * SZ),                             // 4 5
+      "l"(ts.pc + (size_t)t * a.c_ts * SZ), "l"(ts.px + tB * N),                                               // 6 7
+      "l"(ts.pu + tB * M), "l"(ts.pf + (size_t)t * a.f_ts * SZ), "l"(ts.plo + tB * M), "l"(ts.phi + tB * M),  // 8..11
+      "r"(needF), "r"(needf), "r"(has_tb),                                                                     // 12 13 14
+      "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),      // 15..21
+      "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)                 // 22..26
+      : "memory");
+}
+
+template <typename R, int N, int M>
+MPCB_DEV TileSrc tile_src(const StepArgs& a, int b0, int cnt, unsigned char* wbase) {
+  using K = Step2Cfg<R, N, M>;
+  constexpr int P = K::P, SZ = K::SZ;
+  const size_t eb = (size_t)b0 * SZ;
+  TileSrc ts;
+  ts.pC = (const char*)a.C + eb * (P * P);
+  ts.pF = (const char*)a.F + eb * (N * P);
+  ts.pc = (const char*)a.c + eb * P;
+  ts.px = (const char*)a.cur_x + eb * N;
+  ts.pu = (const char*)a.cur_u + eb * M;
+  ts.pf = (const char*)a.f + eb * N;
+  ts.plo = (const char*)a.u_lower + eb * M;
+  ts.phi = (const char*)a.u_upper + eb * M;
+  ts.ucnt = (uint32_t)cnt * SZ;
+  ts.stage0 = smem_u32(wbase + K::HDR_BYTES);
+  ts.bar0 = smem_u32(wbase);
+  return ts;
+}
+
+template <typename R, int N, int M, int MODE, bool KSM, bool PROD>
+__global__ void __launch_bounds__(PROD ? (Step2Cfg<R, N, M>::NWC_PROD + 1) * 32 : Step2Cfg<R, N, M>::NW * 32)
+    __maxnreg__((Step2Cfg<R, N, M>::MAX_REGS))
 lqr_step2_kernel(const StepArgs a) {
   using K = Step2Cfg<R, N, M>;
   constexpr int P = K::P, L = K::L, NXL = K::NXL, PPW = K::PPW, S = K::S, SZ = K::SZ, KT = K::KT, VSTR = K::VSTR, NV = K::NV;
   constexpr int EA = K::EA, A_N = K::A_N, A_M = K::A_M;
+  constexpr int NWC = PROD ? K::NWC_PROD : K::NW;            // consumer warps per CTA
   constexpr unsigned FULLM = (1u << M) - 1u;
   constexpr bool BOX = MODE == MODE_BOX;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = K::NW == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int warp = (NWC == 1 && !PROD) ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int T = a.T, B = a.B;
-  const int gw = blockIdx.x * K::NW + warp;                 // global warp index
+  const int has_tb = (BOX && a.bounds_kind == 2) ? 1 : 0;
+  // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
+  const int G = T + (a.do_rollout ? T : 0);
+  const size_t wsm = K::warp_smem_bytes(T, KSM);
+
+  if constexpr (PROD) {
+    // ---------------------------------------------------------------- producer variant
+    // NWC consumer warps + ONE producer warp per CTA.  The ~40 uniform-datapath instructions of a tile issue
+    // (360 cycles per step, measured) leave the consumers' dependent chain; a consumer only arrives on the
+    // stage's `empty` mbarrier when it is done reading it.
+    if (warp < NWC && lane == 0) {
+      uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * wsm);
+#pragma unroll
+      for (int s2 = 0; s2 < 2 * S; ++s2) mbar_init(&bars[s2], 1);      // full[S], empty[S]
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == NWC) {
+      TileSrc ts[NWC];
+      bool live[NWC];
+#pragma unroll
+      for (int w = 0; w < NWC; ++w) {
+        const int b0w = (blockIdx.x * NWC + w) * PPW;
+        live[w] = b0w < B;
+        ts[w] = tile_src<R, N, M>(a, live[w] ? b0w : 0, live[w] ? min(PPW, B - b0w) : 0, smem_raw + (size_t)w * wsm);
+      }
+      int s2 = 0;
+      uint32_t eph = 1u;                                      // parity of the previous use of the stage
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int w = 0; w < NWC; ++w) {
+          if (!live[w]) continue;
+          if (g >= S) mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (size_t)w * wsm) + S + s2, eph);
+          tile_issue<R, N, M>(ts[w], a, s2, g < T ? T - 1 - g : g - T, g >= T, has_tb);
+        }
+        if (++s2 == S) { s2 = 0; eph ^= 1u; }
+      }
+      return;
+    }
+  }
+  const int gw = blockIdx.x * NWC + warp;                   // global (consumer) warp index
   const int b0 = gw * PPW;
-  if (b0 >= B) return;                                      // warps are independent: no CTA-wide barrier below
+  if (b0 >= B) return;                                      // consumer warps are independent of each other
   const int cnt = min(PPW, B - b0);
-  unsigned char* wbase = smem_raw + (size_t)warp * K::warp_smem_bytes(T, KSM);
+  unsigned char* wbase = smem_raw + (size_t)warp * wsm;
   uint64_t* full = reinterpret_cast<uint64_t*>(wbase);
+  uint64_t* empty = full + S;                               // used by the producer variant only
   unsigned char* stage_base = wbase + K::HDR_BYTES;
   R* scratch = reinterpret_cast<R*>(stage_base + (size_t)S * K::STAGE_BYTES);
   R* kstore = scratch + (size_t)PPW * K::SCRS;
@@ -203,71 +323,35 @@ lqr_step2_kernel(const StepArgs a) {
 
   // ------------------------------------------------------------------ tile streaming (this warp's own ring)
   // One tile = the warp's spans of C[t], F[t], c[t], x_bar[t], u_bar[t] (+ f[t] in the rollout, + tensor
-  // bounds): up to eight 1-D bulk copies onto ONE mbarrier.  The issue is branch free - one elected lane arrives
-  // with the byte count and starts the copies (predicated PTX; UBLKCP executes once per warp) - so the scheduler
-  // overlaps it with the scalar solve that follows the products.  Nothing on the data path goes through the
-  // load/store scoreboards (global loads that are prefetched across loop iterations end up sharing a
+  // bounds): up to eight 1-D bulk copies onto ONE mbarrier (tile_issue).  Nothing on the data path goes through
+  // the load/store scoreboards (global loads that are prefetched across loop iterations end up sharing a
   // scoreboard with the mbarrier probe and expose the full DRAM latency every step - measured).
-  const size_t eb = (size_t)b0 * SZ;
-  const char* pC = (const char*)a.C + eb * (P * P);
-  const char* pF = (const char*)a.F + eb * (N * P);
-  const char* pc = (const char*)a.c + eb * P;
-  const char* px = (const char*)a.cur_x + eb * N;
-  const char* pu = (const char*)a.cur_u + eb * M;
-  const char* pf = (const char*)a.f + eb * N;
-  const char* plo = (const char*)a.u_lower + eb * M;
-  const char* phi = (const char*)a.u_upper + eb * M;
-  const size_t strB = (size_t)B * SZ;                       // bytes per time step and per element of a problem
-  const uint32_t ucnt = (uint32_t)cnt * SZ;                 // bytes per element-of-a-problem over the warp's problems
-  const int has_tb = (BOX && a.bounds_kind == 2) ? 1 : 0;
-  const uint32_t by_base = ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0));
-  if (lane == 0) {
+  const TileSrc tsrc = tile_src<R, N, M>(a, b0, cnt, wbase);
+  if constexpr (!PROD) {
+    if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-    mbar_fence_init();
+      for (int s2 = 0; s2 < S; ++s2) mbar_init(&full[s2], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  const uint32_t stage0 = smem_u32(stage_base), bar0 = smem_u32(full);
-  int iss_s = 0;                                            // stage of the next tile to issue
+  int iss_s = PROD ? G % S : 0;                             // stage of the next tile this warp issues itself
   auto issue = [&](int t, bool fwd) {
-    const uint32_t dst = stage0 + (uint32_t)iss_s * K::STAGE_BYTES;
-    const uint32_t bar = bar0 + (uint32_t)iss_s * 8u;
-    const int needF = t < T - 1 ? 1 : 0;
-    const int needf = (fwd && needF && a.has_f) ? 1 : 0;
-    const size_t tB = (size_t)t * strB;
-    asm volatile(
-        "{\n\t.reg .pred P, PF, Pf, PB;\n\t.reg .b32 d, n;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "setp.ne.and.b32 PF, %12, 0, P;\n\t"
-        "setp.ne.and.b32 Pf, %13, 0, P;\n\t"
-        "setp.ne.and.b32 PB, %14, 0, P;\n\t"
-        "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
-        "mul.lo.u32 n, %3, %15;\n\t"
-        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
-        "mul.lo.u32 n, %3, %16;\n\tadd.u32 d, %2, %17;\n\t"
-        "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%5], n, [%0];\n\t"
-        "mul.lo.u32 n, %3, %18;\n\tadd.u32 d, %2, %19;\n\t"
-        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%6], n, [%0];\n\t"
-        "mul.lo.u32 n, %3, %20;\n\tadd.u32 d, %2, %21;\n\t"
-        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%7], n, [%0];\n\t"
-        "add.u32 d, %2, %23;\n\t"
-        "@Pf cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%9], n, [%0];\n\t"
-        "mul.lo.u32 n, %3, %22;\n\tadd.u32 d, %2, %24;\n\t"
-        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%8], n, [%0];\n\t"
-        "add.u32 d, %2, %25;\n\t"
-        "@PB cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%10], n, [%0];\n\t"
-        "add.u32 d, %2, %26;\n\t"
-        "@PB cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%11], n, [%0];\n\t"
-        "}" ::"r"(bar),                                                                    // 0
-        "r"(by_base + (needF ? ucnt * (N * P) : 0u) + (needf ? ucnt * N : 0u)),             // 1
-        "r"(dst), "r"(ucnt),                                                                 // 2 3
-        "l"(pC + (size_t)t * a.C_ts * SZ), "l"(pF + (size_t)t * a.F_ts * SZ), "l"(pc + (size_t)t * a.c_ts * SZ), "l"(px + tB * N),  // 4 5 6 7
-        "l"(pu + tB * M), "l"(pf + (size_t)t * a.f_ts * SZ), "l"(plo + tB * M), "l"(phi + tB * M),     // 8 9 10 11
-        "r"(needF), "r"(needf), "r"(has_tb),                                                 // 12 13 14
-        "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),   // 15..21
-        "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)              // 22..26
-        : "memory");
+    tile_issue<R, N, M>(tsrc, a, iss_s, t, fwd, has_tb);
     iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
+  };
+  // "done with the stage of tile g": self-feeding warps refill it with tile g + S, the producer variant
+  // tells the producer (one lane arrives on the stage's empty barrier)
+  auto release = [&](int g) {
+    if constexpr (PROD) {
+      if (lane == 0) mbar_arrive(&empty[g % S]);
+    } else {
+      const int gn = g + S;
+      if (gn < G) {
+        if (gn < T) issue(T - 1 - gn, false);
+        else issue(gn - T, true);
+      }
+    }
   };
   int con_s = 0;                                            // stage / phase parity of the next tile to consume
   uint32_t con_ph = 0;
@@ -279,13 +363,9 @@ lqr_step2_kernel(const StepArgs a) {
     if (++con_s == S) { con_s = 0; con_ph ^= 1u; }
     return st;
   };
-  // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
-  const int G = T + (a.do_rollout ? T : 0);
-  auto issue_g = [&](int g) {
-    if (g < T) issue(T - 1 - g, false);
-    else issue(g - T, true);
-  };
-  for (int g = 0; g < S && g < G; ++g) issue_g(g);
+  if constexpr (!PROD) {
+    for (int g = 0; g < S && g < G; ++g) release(g - S);     // prologue: tiles 0 .. S-1
+  }
 
   const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
   auto mask_bits = [&](int t) -> unsigned {               // u_zero_I of (t, problem): M bytes, straight from global
@@ -401,10 +481,7 @@ lqr_step2_kernel(const StepArgs a) {
     TICK2(tk, 2)
     // tile t is consumed (its C pair / rows / vectors were read by pre(t)): refill the stage with tile g + S
     __syncwarp();
-    {
-      const int g = (T - 1 - t) + S;
-      if (g < G) issue_g(g);
-    }
+    release(T - 1 - t);
     const R* st_next = st;
     if (t > 0) {                                   // F column pair of step t-1: lands while the solve runs
       st_next = acquire(ok_next);
@@ -739,7 +816,8 @@ lqr_step2_kernel(const StepArgs a) {
       if (t < T - 1) load_span<R, N, EA>(xs + (t & 1) * NV, xr);
       TICK2(tf, 3)
       // tile t is consumed (its operands were loaded one step ago): refill its stage
-      if (t + S < T) issue(t + S, true);
+      if (pass == 0) release(T + t);
+      else if (t + S < T) issue(t + S, true);
       st = st_next;
       TICK2(tf, 4)
     }
@@ -776,29 +854,29 @@ template <typename R, int N, int M, int MODE>
 int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
   using K = Step2Cfg<R, N, M>;
   StepArgs a = args;
+  const bool prod = a.impl == 3 || (a.impl != 2 && K::PRODUCER_DEFAULT);
+  const int nwc = prod ? K::NWC_PROD : K::NW;
   a.k_in_smem = 1;
-  size_t smem = K::smem_bytes(a.T, true);
+  size_t smem = (size_t)nwc * K::warp_smem_bytes(a.T, true);
   const bool have_ws = a.Ks != nullptr && a.ks != nullptr;
   // keep a few warps per SM resident: move the gain store to the caller's buffer when it is what limits them
   const bool crowded = K::warp_smem_bytes(a.T, true) > (size_t)max_smem_optin / 6;
   if (smem > (size_t)max_smem_optin || (crowded && have_ws && a.do_rollout)) {
     a.k_in_smem = 0;
-    smem = K::smem_bytes(a.T, false);
+    smem = (size_t)nwc * K::warp_smem_bytes(a.T, false);
     if (smem > (size_t)max_smem_optin) return 4;
     if (a.do_rollout && !have_ws) return 4;
   }
   const int warps = (a.B + K::PPW - 1) / K::PPW;
-  const int grid = (warps + K::NW - 1) / K::NW;
-  if (a.k_in_smem) {
-    auto kern = lqr_step2_kernel<R, N, M, MODE, true>;
+  const int grid = (warps + nwc - 1) / nwc;
+  const int threads = prod ? (nwc + 1) * 32 : nwc * 32;
+  auto go = [&](auto kern) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
-    kern<<<grid, K::NW * 32, smem, stream>>>(a);
-  } else {
-    auto kern = lqr_step2_kernel<R, N, M, MODE, false>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
-    kern<<<grid, K::NW * 32, smem, stream>>>(a);
-  }
-  return cudaGetLastError() == cudaSuccess ? 0 : 5;
+    kern<<<grid, threads, smem, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : 5;
+  };
+  if (a.k_in_smem) return prod ? go(lqr_step2_kernel<R, N, M, MODE, true, true>) : go(lqr_step2_kernel<R, N, M, MODE, true, false>);
+  return prod ? go(lqr_step2_kernel<R, N, M, MODE, false, true>) : go(lqr_step2_kernel<R, N, M, MODE, false, false>);
 }
 
 template <typename R, int N, int M>
