@@ -334,11 +334,12 @@ def extras(dev, stream, sh, peak):
     lv = [inp[k].clone().requires_grad_(True) for k in ("x_init", "C", "c", "F", "f")]
     wx, wu = torch.randn_like(inp["cur_x"]), torch.randn_like(inp["cur_u"])
 
-    def adjoint(_sh=None):
-        fn = LQRStep(8, 2, 20, true_cost=QuadCost(lv[1], lv[2]), true_dynamics=LinDx(lv[3], lv[4]),
-                     current_x=inp["cur_x"], current_u=inp["cur_u"], no_op_forward=True)
-        xo, uo = fn(*lv)
-        return torch.autograd.grad((xo * wx).sum() + (uo * wu).sum(), lv)
+    fn = LQRStep(8, 2, 20, true_cost=QuadCost(lv[1], lv[2]), true_dynamics=LinDx(lv[3], lv[4]),
+                 current_x=inp["cur_x"], current_u=inp["cur_u"], no_op_forward=True)
+    xo, uo = fn(*lv)
+
+    def adjoint(_sh=None):          # LQRStepFn.backward through autograd, upstream gradients given directly
+        return torch.autograd.grad((xo, uo), lv, (wx, wu), retain_graph=True)
     l0 = _lib.launch_count()
     adjoint()
     n_kernels = _lib.launch_count() - l0
@@ -347,7 +348,7 @@ def extras(dev, stream, sh, peak):
     res["adjoint_config3_api"] = {"us_per_backward": round(us, 2), "solves_per_s": 4096 / (us * 1e-6),
                                   "bytes_per_solve": ab, "hbm_frac": ab * 4096 / (us * 1e-6) / 1e9 / peak,
                                   "kernels_per_backward": int(n_kernels),
-                                  "api": "LQRStep(no_op_forward=True)(...) + torch.autograd.grad of a weighted sum (includes the loss kernels and the autograd / Python host path)"}
+                                  "api": "torch.autograd.grad through LQRStep(no_op_forward=True)(...): the autograd engine + LQRStepFn.backward (Python host path included)"}
     raws = [RawAdjoint(s, s["cur_x"], s["cur_u"], 4096, 20, 8, 2) for s in sets3]
     us = time_launches(raws, 20, stream, sh)
     res["adjoint_config3_c_abi"] = {"us_per_backward": round(us, 2), "solves_per_s": 4096 / (us * 1e-6),

@@ -190,6 +190,31 @@ def main():
             x=xs, u=us, costs=costs, wx=wx, wu=wu,
             dx_init=grads[0], dC=grads[1], dc=grads[2], dF=grads[3], df=grads[4])
 
+    # ---------------------------------------------------------------- slew-rate penalty (reference mpc/mpc.py:362-445)
+    # (the reference's slew branch only works with Module dynamics: for LinDx it passes true_dynamics=None, :411-414)
+    class AffineDx(torch.nn.Module):
+        def __init__(self, A, Bm):
+            super().__init__()
+            self.A, self.Bm = A, Bm
+
+        def forward(self, x, u):
+            return x @ self.A.t() + u @ self.Bm.t()
+
+    for name, seed, B, T, n, m, pen, bounds, with_prev in [("slew_box_f64", 301, 3, 7, 3, 2, 0.5, 0.4, True),
+                                                            ("slew_unb_f64", 302, 2, 6, 4, 2, 2.0, None, False)]:
+        C, c, _, _, x0 = gen_problem(seed, B, T, n, m, torch.float64, False, True)
+        g = torch.Generator().manual_seed(seed + 1)
+        A = 0.9 * torch.eye(n, dtype=torch.float64) + 0.1 * torch.randn(n, n, generator=g, dtype=torch.float64) / n ** 0.5
+        Bm = torch.randn(n, m, generator=g, dtype=torch.float64) / n ** 0.5
+        prev = 0.2 * torch.randn(B, m, generator=g, dtype=torch.float64) if with_prev else None
+        ul, uu = (None, None) if bounds is None else (-bounds, bounds)
+        with contextlib.redirect_stdout(io.StringIO()):
+            xs, us, costs = rmpc.MPC(n, m, T, u_lower=ul, u_upper=uu, lqr_iter=15, verbose=-1, exit_unconverged=False,
+                                     detach_unconverged=False, slew_rate_penalty=pen, prev_ctrl=prev, eps=1e-9,
+                                     grad_method=rmpc.GradMethods.AUTO_DIFF)(
+                x0, rmpc.QuadCost(C, c), AffineDx(A, Bm))
+        npz(name, C=C, c=c, A=A, Bm=Bm, x_init=x0, bound=bounds, penalty=pen, prev_ctrl=prev, x=xs, u=us, costs=costs)
+
     # ---------------------------------------------------------------- TV-LQR notebook trace
     # examples/Time Varying Linear-Quadratic Control.ipynb (cell 2); its recorded output
     # is the only golden output stored inside the reference tree.

@@ -89,6 +89,33 @@ def test_slew_rate_penalty():
     assert rough(u2_) < rough(u0_)
 
 
+@pytest.mark.parametrize("name", ["slew_box_f64", "slew_unb_f64"])
+def test_slew_rate_matches_reference_fixture(name):
+    """The slew-rate augmentation (state = [u_{t-1}; x], reference mpc/mpc.py:362-445) against trajectories the
+    unmodified reference produced for the same inputs (oracle/make_golden.py), float64."""
+    from mpc import mpc
+    g = load_golden(name)
+    T, B, p = g["C"].shape[0], g["C"].shape[1], g["C"].shape[2]
+    n = g["x_init"].shape[1]
+    m = p - n
+    bound = g.get("bound")
+    kw = {} if bound is None else dict(u_lower=-float(bound), u_upper=float(bound))
+    prev = g["prev_ctrl"].to(DEV) if "prev_ctrl" in g else None
+    A, Bm = g["A"].to(DEV), g["Bm"].to(DEV)
+
+    class AffineDx(torch.nn.Module):        # the reference's slew branch needs Module dynamics (mpc/mpc.py:411-414)
+        def forward(self, xx, uu):
+            return xx @ A.t() + uu @ Bm.t()
+
+    x, u, costs = mpc.MPC(n, m, T, lqr_iter=15, verbose=-1, exit_unconverged=False, detach_unconverged=False,
+                          slew_rate_penalty=float(g["penalty"]), prev_ctrl=prev, eps=1e-9,
+                          grad_method=mpc.GradMethods.AUTO_DIFF, **kw)(
+        g["x_init"].to(DEV), mpc.QuadCost(g["C"].to(DEV), g["c"].to(DEV)), AffineDx())
+    tol = 2e-4 if bound is not None else 1e-8          # bounded: pnqp step tolerance (batch-coupled reference)
+    assert maxdiff(u, g["u"]) < tol and maxdiff(x, g["x"]) < tol
+    assert maxdiff(costs, g["costs"]) < 10 * tol * max(1.0, float(g["costs"].abs().max()))
+
+
 def test_cartpole_ilqr_matches_reference_fixture():
     """BASELINE config 2 recipe (small): nonlinear Module dynamics, AUTO_DIFF linearisation, bounds +-100,
     decay .5, 2 line-search iterations, eps 1e-2 - against the reference's stored trajectory."""
