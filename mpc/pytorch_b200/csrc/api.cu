@@ -83,12 +83,19 @@ static int check_dims(const mpcb200_dims* d) {
   return MPCB200_OK;
 }
 
+struct AdjExtra {      // fused-adjoint request riding on a step launch (api-internal)
+  const void *c, *x, *u;
+  void *dC, *dc, *dF, *df, *dx_init;
+  int has_df, ok;
+  long long c_ts;
+};
+
 template <typename R>
 static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C, const R* c, const R* F,
                      const R* f, const R* x_init, const R* cur_x, const R* cur_u, const R* u_lower,
                      const R* u_upper, const uint8_t* u_zero_I, R* new_x, R* new_u, R* costs,
                      R* full_du_norm, R* alphas, R* du_first, int32_t* qp_iters, uint8_t* free_mask, int32_t* status,
-                     R* Ks, R* ks, void* stream) {
+                     R* Ks, R* ks, void* stream, const AdjExtra* adj = nullptr) {
   int rc = check_dims(d);
   if (rc) return rc;
   if (p == nullptr || C == nullptr || c == nullptr || cur_x == nullptr || cur_u == nullptr)
@@ -149,7 +156,14 @@ static int step_impl(const mpcb200_dims* d, const mpcb200_params* p, const R* C,
     if (!shape_ok) return MPCB200_ERR_BAD_DIMS;
     for (int i = 0; i < 8; ++i) a.dp.p[i] = p->dyn[i];
   }
-  if (const char* k = std::getenv("MPCB200_KERNEL")) a.impl = std::atoi(k);   // developer A/B knob: 1 generic, 2 pair
+  if (const char* k = std::getenv("MPCB200_KERNEL")) a.impl = std::atoi(k);
+  if (adj != nullptr) {          // fused KKT adjoint: column-pair kernel only
+    if (!adj->ok || !a.bulk_ok || a.impl == 1) return MPCB200_ERR_UNSUPPORTED_DIMS;
+    a.impl = 2;
+    a.adj = 1; a.adj_has_df = adj->has_df; a.adj_c = adj->c; a.adj_x = adj->x; a.adj_u = adj->u;
+    a.adj_dC = adj->dC; a.adj_dc = adj->dc; a.adj_dF = adj->dF; a.adj_df = adj->df; a.adj_dx_init = adj->dx_init;
+    a.adj_c_ts = adj->c_ts;
+  }   // developer A/B knob: 1 generic, 2 pair
   rc = (sizeof(R) == 4 ? e->step32 : e->step64)(a, smem, (cudaStream_t)stream);
   if (rc == 0) g_launches.fetch_add(1);
   return rc;
@@ -266,6 +280,20 @@ static int adjoint_impl(const mpcb200_dims* d, const mpcb200_params* p, const R*
   R* zx = zeros;
   R* zu = zeros + TB * d->n;
   R* z0 = zu + TB * d->m;
+  // Preferred: ONE launch of the column-pair kernel doing solve + costates + outer products (C, F read from HBM
+  // once, d tau kept in shared memory).  Shapes / alignments it does not take fall through to the 3-launch path.
+  {
+    AdjExtra ax;
+    ax.c = c; ax.x = new_x; ax.u = new_u; ax.dC = dC; ax.dc = dc; ax.dF = dF; ax.df = d->has_f ? df : nullptr;
+    ax.dx_init = dx_init; ax.has_df = d->has_f ? 1 : 0;
+    ax.c_ts = tstride(d->c_tstride, (long long)d->B * (d->n + d->m));
+    ax.ok = aligned16(c) && aligned16(new_x) && aligned16(new_u) && (ax.c_ts * (long long)sizeof(R)) % 16 == 0;
+    rc = step_impl<R>(&ds, &ps, C, negr, F, (const R*)nullptr, z0, zx, zu, (const R*)nullptr, (const R*)nullptr, mask,
+                      dxs, dus, scal, scal + d->B, scal + 2 * d->B, (R*)nullptr, (int32_t*)nullptr,
+                      (uint8_t*)nullptr, (int32_t*)nullptr, (R*)nullptr, (R*)nullptr, stream, &ax);
+    if (rc == 0) return 0;
+    if (rc != MPCB200_ERR_UNSUPPORTED_DIMS && rc != MPCB200_ERR_SMEM) return rc;
+  }
   rc = step_impl<R>(&ds, &ps, C, negr, F, (const R*)nullptr, z0, zx, zu, (const R*)nullptr, (const R*)nullptr, mask,
                     dxs, dus, scal, scal + d->B, scal + 2 * d->B, (R*)nullptr, (int32_t*)nullptr,
                     (uint8_t*)nullptr, (int32_t*)nullptr, (R*)nullptr, (R*)nullptr, stream);

@@ -55,6 +55,12 @@ struct StepArgs {
   int k_in_smem;  // gains of all T steps fit in shared memory
   int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh), 3 pair + producer warp
   long long C_ts, c_ts, F_ts, f_ts;   // elements between consecutive time slices of C, c, F, f (0 = time invariant)
+  // fused KKT adjoint (column-pair kernel only): after the masked solve, a third sweep computes the costates and
+  // writes dC, dc, dF, df, dx_init; `c` carries -r, the x_bar/u_bar tile slots carry the forward solution tau*
+  int adj, adj_has_df;
+  const void *adj_c, *adj_x, *adj_u;
+  void *adj_dC, *adj_dc, *adj_dF, *adj_df, *adj_dx_init;
+  long long adj_c_ts;
   int dyn_kind;   // true dynamics of the rollout: DYN_LINEAR (F,f) or a known system evaluated in the kernel
   DynParams dp;
 };

@@ -126,7 +126,8 @@ struct Step2Cfg {
   static constexpr int OFF_f = OFF_u + PPW * M;
   static constexpr int OFF_lo = OFF_f + PPW * N;
   static constexpr int OFF_hi = OFF_lo + PPW * M;
-  static constexpr int OFF_END = OFF_hi + PPW * M;
+  static constexpr int OFF_c2 = OFF_hi + PPW * M;        // fused adjoint: the true cost's c (the c slot carries -r)
+  static constexpr int OFF_END = OFF_c2 + PPW * P;
   static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
   // ring depth.  Measured for n=16, m=4 (9.3 KB tiles): 2 stages + a 200-register cap (9 warps / SM instead of 5)
   // is SLOWER (688 vs 449 us at B=4096, 1953 vs 1463 us at B=16384): the spills and the single tile of
@@ -155,9 +156,10 @@ struct Step2Cfg {
   }
   static constexpr int SCRS = pick_scr();
   static constexpr int HDR_BYTES = 128;                  // S mbarriers (per warp)
-  __host__ __device__ static size_t warp_smem_bytes(int T, bool k_in_smem) {
+  __host__ __device__ static size_t warp_smem_bytes(int T, bool k_in_smem, bool adj = false) {
     size_t b = HDR_BYTES + (size_t)S * STAGE_BYTES + (size_t)PPW * SCRS * SZ;
     if (k_in_smem) b += (size_t)PPW * T * KT * SZ;
+    if (adj) b += (size_t)PPW * T * P * SZ;              // d tau of every step, kept for the costate sweep
     return round_up((int)b, 128);
   }
   static size_t smem_bytes(int T, bool k_in_smem) { return (size_t)NW * warp_smem_bytes(T, k_in_smem); }
@@ -171,7 +173,7 @@ struct Step2Cfg {
 
 // One warp's tile stream: where its spans start in global memory and where its ring lives in shared memory.
 struct TileSrc {
-  const char *pC, *pF, *pc, *px, *pu, *pf, *plo, *phi;
+  const char *pC, *pF, *pc, *px, *pu, *pf, *plo, *phi, *pc2;
   uint32_t ucnt;      // bytes per element-of-a-problem over the warp's problems (cnt * sizeof(R))
   uint32_t stage0;    // shared address of stage 0
   uint32_t bar0;      // shared address of full[0]
@@ -189,8 +191,8 @@ MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t,
   const int needF = t < a.T - 1 ? 1 : 0;
   const int needf = (fwd && needF && a.has_f) ? 1 : 0;
   const size_t tB = (size_t)t * a.B * SZ;
-  const uint32_t total = ts.ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0)) + (needF ? ts.ucnt * (N * P) : 0u) +
-                         (needf ? ts.ucnt * N : 0u);
+  const uint32_t total = ts.ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0) + (a.adj ? P : 0)) +
+                         (needF ? ts.ucnt * (N * P) : 0u) + (needf ? ts.ucnt * N : 0u);
   asm volatile(
       "{\n\t.reg .pred P, PF, Pf, PB;\n\t.reg .b32 d, n;\n\t"
       "elect.sync _|P, 0xffffffff;\n\t"
@@ -222,6 +224,14 @@ MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t,
       "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),      // 15..21
       "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)                 // 22..26
       : "memory");
+  if (a.adj) {      // fused adjoint: the true cost's c rides on the same mbarrier (its bytes are in `total`)
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t"
+        "}" ::"r"(bar), "r"(dst + (uint32_t)K::OFF_c2 * SZ), "l"(ts.pc2 + (size_t)t * a.adj_c_ts * SZ), "r"(ts.ucnt * P)
+        : "memory");
+  }
 }
 
 template <typename R, int N, int M>
@@ -233,8 +243,9 @@ MPCB_DEV TileSrc tile_src(const StepArgs& a, int b0, int cnt, unsigned char* wba
   ts.pC = (const char*)a.C + eb * (P * P);
   ts.pF = (const char*)a.F + eb * (N * P);
   ts.pc = (const char*)a.c + eb * P;
-  ts.px = (const char*)a.cur_x + eb * N;
-  ts.pu = (const char*)a.cur_u + eb * M;
+  ts.px = (const char*)(a.adj ? a.adj_x : a.cur_x) + eb * N;      // adjoint: the nominal point is zero, the slots carry tau*
+  ts.pu = (const char*)(a.adj ? a.adj_u : a.cur_u) + eb * M;
+  ts.pc2 = (const char*)a.adj_c + eb * P;
   ts.pf = (const char*)a.f + eb * N;
   ts.plo = (const char*)a.u_lower + eb * M;
   ts.phi = (const char*)a.u_upper + eb * M;
@@ -244,7 +255,7 @@ MPCB_DEV TileSrc tile_src(const StepArgs& a, int b0, int cnt, unsigned char* wba
   return ts;
 }
 
-template <typename R, int N, int M, int MODE, bool KSM, bool PROD>
+template <typename R, int N, int M, int MODE, bool KSM, bool PROD, bool ADJ = false>
 __global__ void __launch_bounds__(PROD ? (Step2Cfg<R, N, M>::NWC_PROD + 1) * 32 : Step2Cfg<R, N, M>::NW * 32)
     __maxnreg__((Step2Cfg<R, N, M>::MAX_REGS))
 lqr_step2_kernel(const StepArgs a) {
@@ -260,7 +271,7 @@ lqr_step2_kernel(const StepArgs a) {
   const int has_tb = (BOX && a.bounds_kind == 2) ? 1 : 0;
   // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
   const int G = T + (a.do_rollout ? T : 0);
-  const size_t wsm = K::warp_smem_bytes(T, KSM);
+  const size_t wsm = K::warp_smem_bytes(T, KSM, ADJ);
 
   if constexpr (PROD) {
     // ---------------------------------------------------------------- producer variant
@@ -307,6 +318,7 @@ lqr_step2_kernel(const StepArgs a) {
   unsigned char* stage_base = wbase + K::HDR_BYTES;
   R* scratch = reinterpret_cast<R*>(stage_base + (size_t)S * K::STAGE_BYTES);
   R* kstore = scratch + (size_t)PPW * K::SCRS;
+  R* dts_all = kstore + (KSM ? (size_t)PPW * T * KT : 0);   // ADJ: d tau store, [problem][t][P]
 
   const bool writer_lane = lane < PPW * L;
   const int pi = writer_lane ? lane / L : PPW - 1;
@@ -415,10 +427,16 @@ lqr_step2_kernel(const StepArgs a) {
   auto pre = [&](int tt, const R* stt) {
 #pragma unroll
     for (int i = 0; i < P; ++i) Qp[i] = ld_pair<R>(stt + oC + i * P + c0);
-    R Cr0[P], Cr1[P], tb[P];
-    load_span<R, P, EA>(stt + oC + c0 * P, Cr0);            // c0 * P is a multiple of 4
-    load_span<R, P, 2>(stt + oC + (c0 + 1) * P, Cr1);
-    {
+    const P2<R> cj = ld_pair<R>(stt + oc + c0);
+    R tb[P];
+    if constexpr (ADJ) {         // KKT adjoint: the nested solve starts from the zero trajectory (c_back = c, cost 0);
+#pragma unroll                 // the x_bar / u_bar slots of the tile carry tau* for the costate sweep instead
+      for (int i = 0; i < P; ++i) tb[i] = R(0);
+      qp = cj;
+    } else {
+      R Cr0[P], Cr1[P];
+      load_span<R, P, EA>(stt + oC + c0 * P, Cr0);            // c0 * P is a multiple of 4
+      load_span<R, P, 2>(stt + oC + (c0 + 1) * P, Cr1);
       R tx[N], tu[M];
       load_span<R, N, A_N>(stt + ox, tx);
       load_span<R, M, A_M>(stt + ou, tu);
@@ -426,13 +444,12 @@ lqr_step2_kernel(const StepArgs a) {
       for (int i = 0; i < N; ++i) tb[i] = tx[i];
 #pragma unroll
       for (int q = 0; q < M; ++q) tb[N + q] = tu[q];
+      const P2<R> tj = ld_pair<R>(stt + (isx ? ox + c0 : ou + ua0));   // tau_bar[c0], tau_bar[c0+1]
+      R ct0, ct1;
+      dot2_span<R, P>(Cr0, Cr1, tb, ct0, ct1);                 // rows c0, c0+1 of C tau_bar (lqr_step.py:289-295)
+      if (writer_lane) oldcost_part += tj.x * (R(0.5) * ct0 + cj.x) + tj.y * (R(0.5) * ct1 + cj.y);   // util.get_cost (:169)
+      qp = {ct0 + cj.x, ct1 + cj.y};
     }
-    const P2<R> cj = ld_pair<R>(stt + oc + c0);
-    const P2<R> tj = ld_pair<R>(stt + (isx ? ox + c0 : ou + ua0));   // tau_bar[c0], tau_bar[c0+1]
-    R ct0, ct1;
-    dot2_span<R, P>(Cr0, Cr1, tb, ct0, ct1);                 // rows c0, c0+1 of C tau_bar (lqr_step.py:289-295)
-    if (writer_lane) oldcost_part += tj.x * (R(0.5) * ct0 + cj.x) + tj.y * (R(0.5) * ct1 + cj.y);   // util.get_cost (:169)
-    qp = {ct0 + cj.x, ct1 + cj.y};
 #pragma unroll
     for (int q = 0; q < M; ++q) {
       ubar[q] = tb[N + q];
@@ -718,8 +735,15 @@ lqr_step2_kernel(const StepArgs a) {
         load_span<R, P, EA>(stt + oF + xr0 * P, Fr0);
         load_span<R, P, 2>(stt + oF + (xr0 + 1) * P, Fr1);
       }
-      load_span<R, N, A_N>(stt + ox, tbx);
-      load_span<R, M, A_M>(stt + ou, tbu);
+      if constexpr (ADJ) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) tbx[i] = R(0);
+#pragma unroll
+        for (int q = 0; q < M; ++q) tbu[q] = R(0);
+      } else {
+        load_span<R, N, A_N>(stt + ox, tbx);
+        load_span<R, M, A_M>(stt + ou, tbu);
+      }
       cj = ld_pair<R>(stt + oc + c0);
       fj = {R(0), R(0)};
       if (a.has_f && tt < T - 1) fj = ld_pair<R>(stt + of_ + xr0);
@@ -804,6 +828,9 @@ lqr_step2_kernel(const StepArgs a) {
           if (pass == 0 && gdu1 != nullptr) st_pair(gdu1 + orow * M + ua0, P2<R>{ubj.x - tj.x, ubj.y - tj.y});
         }
       }
+      if constexpr (ADJ) {                          // d tau_t of this pass, for the costate sweep
+        if (writer_lane) st_pair(dts_all + ((size_t)pi * T + t) * P + c0, tj);
+      }
       TICK2(tf, 2)
       // operands of step t+1 into the (now dead) registers of step t
       const R* st_next = st;
@@ -840,6 +867,96 @@ lqr_step2_kernel(const StepArgs a) {
            gw, T, tk[2] / T, tk[7] / T, tk[3] / T, tk[4] / T, tk[5] / T, tk[6] / T, tk[1] / T,
            tf[1] / T, tf[2] / T, tf[3] / T, tf[4] / T);
 #endif
+  if constexpr (ADJ) {
+    // ======================= costates and outer products (lqr_step.py:342-404) =======================
+    // Third sweep, t = T-1 .. 0, over the same tiles (C, F, -r in the c slot, the true c, tau* in the x_bar/u_bar
+    // slots; L2 hits) with d tau of every step in shared memory:
+    //   lambda_t  = C^x_t tau*_t + c^x_t + F^x_t' lambda_{t+1},   dlambda_t = C^x_t dtau_t - r^x_t + F^x_t' dlambda_{t+1}
+    //   dC_t = -1/2 (dtau tau*' + tau* dtau'),  dc_t = -dtau_t,  dF_t = -(dlambda_{t+1} tau*' + lambda_{t+1} dtau'),
+    //   df_t = -dlambda_{t+1},  dx_init = -dlambda_0.     A lane writes its column pair of every row (8-byte stores).
+    __syncwarp();
+    for (int g = 0; g < S && g < T; ++g) issue(T - 1 - g, false);
+    R* gdC = (R*)a.adj_dC;
+    R* gdc = (R*)a.adj_dc;
+    R* gdF = (R*)a.adj_dF;
+    R* gdf = (R*)a.adj_df;
+    const R* dts = dts_all + (size_t)pi * T * P;
+    const int oc2 = K::OFF_c2 + pi * P;
+    R lam[N], dlam[N];                             // lambda_{t+1}, dlambda_{t+1} replicated on every lane
+#pragma unroll
+    for (int k = 0; k < N; ++k) lam[k] = dlam[k] = R(0);
+    P2<R> dl_own = {R(0), R(0)};                   // dlambda_{t+1}[c0], [c0+1] (x lanes)
+    for (int t = T - 1; t >= 0; --t) {
+      const R* stt = acquire(0u);
+      const size_t tbo = (size_t)t * B + bsafe;
+      R ts_[P], dt_[P];                            // tau*_t, dtau_t replicated
+      {
+        R tx[N], tu[M];
+        load_span<R, N, A_N>(stt + ox, tx);
+        load_span<R, M, A_M>(stt + ou, tu);
+#pragma unroll
+        for (int i = 0; i < N; ++i) ts_[i] = tx[i];
+#pragma unroll
+        for (int q = 0; q < M; ++q) ts_[N + q] = tu[q];
+        load_span<R, P, 2>(dts + (size_t)t * P, dt_);
+      }
+      const P2<R> tsj = ld_pair<R>(stt + (isx ? ox + c0 : ou + ua0));     // tau*[c0], tau*[c0+1]
+      const P2<R> dtj = ld_pair<R>(dts + (size_t)t * P + c0);             // dtau[c0], dtau[c0+1]
+      if (wr) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {              // dC_t[i][pair]
+          P2<R> v = mul2(tsj, P2<R>{dt_[i], dt_[i]});
+          v = fma2s(dtj, ts_[i], v);
+          st_pair(gdC + (tbo * P + i) * P + c0, P2<R>{R(-0.5) * v.x, R(-0.5) * v.y});
+        }
+        st_pair(gdc + tbo * P + c0, P2<R>{-dtj.x, -dtj.y});
+        if (t < T - 1) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) {            // dF_t[k][pair]
+            P2<R> v = mul2(tsj, P2<R>{dlam[k], dlam[k]});
+            v = fma2s(dtj, lam[k], v);
+            st_pair(gdF + (tbo * N + k) * P + c0, P2<R>{-v.x, -v.y});
+          }
+          if (a.adj_has_df && isx) st_pair(gdf + tbo * N + c0, P2<R>{-dl_own.x, -dl_own.y});
+        } else if (a.F_T == T) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) st_pair(gdF + (tbo * N + k) * P + c0, P2<R>{R(0), R(0)});
+        }
+      }
+      // costates of step t: rows c0, c0+1 (x lanes)
+      {
+        R Cr0[P], Cr1[P];
+        load_span<R, P, EA>(stt + oC + xr0 * P, Cr0);
+        load_span<R, P, 2>(stt + oC + (xr0 + 1) * P, Cr1);
+        P2<R> nl, ndl;
+        dot2_span<R, P>(Cr0, Cr1, ts_, nl.x, nl.y);
+        dot2_span<R, P>(Cr0, Cr1, dt_, ndl.x, ndl.y);
+        const P2<R> c2j = ld_pair<R>(stt + oc2 + xr0);       // true c^x
+        const P2<R> nrj = ld_pair<R>(stt + oc + xr0);        // -r^x (the c slot)
+        nl.x += c2j.x; nl.y += c2j.y;
+        ndl.x += nrj.x; ndl.y += nrj.y;
+        if (t < T - 1) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const P2<R> fp = ld_pair<R>(stt + oF + k * P + xr0);        // F[k][c0], F[k][c0+1]
+            nl = fma2s(fp, lam[k], nl);
+            ndl = fma2s(fp, dlam[k], ndl);
+          }
+        }
+        dl_own = ndl;
+        if (writer_lane && isx) {
+          st_pair(xs + c0, nl);
+          st_pair(xs + NV + c0, ndl);
+        }
+      }
+      __syncwarp();
+      load_span<R, N, EA>(xs, lam);
+      load_span<R, N, EA>(xs + NV, dlam);
+      __syncwarp();
+      if (t - S >= 0) issue(t - S, false);
+    }
+    if (wr && isx) st_pair((R*)a.adj_dx_init + (size_t)b * N + c0, P2<R>{-dl_own.x, -dl_own.y});
+  }
   if (worse) alpha /= decay;                                                  // (:252)
   if (wr && lq == 0) {
     ((R*)a.costs)[b] = cost;
@@ -854,16 +971,16 @@ template <typename R, int N, int M, int MODE>
 int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
   using K = Step2Cfg<R, N, M>;
   StepArgs a = args;
-  const bool prod = a.impl == 3 || (a.impl != 2 && K::PRODUCER_DEFAULT);
+  const bool prod = !a.adj && (a.impl == 3 || (a.impl != 2 && K::PRODUCER_DEFAULT));
   const int nwc = prod ? K::NWC_PROD : K::NW;
   a.k_in_smem = 1;
-  size_t smem = (size_t)nwc * K::warp_smem_bytes(a.T, true);
+  size_t smem = (size_t)nwc * K::warp_smem_bytes(a.T, true, a.adj != 0);
   const bool have_ws = a.Ks != nullptr && a.ks != nullptr;
   // keep a few warps per SM resident: move the gain store to the caller's buffer when it is what limits them
-  const bool crowded = K::warp_smem_bytes(a.T, true) > (size_t)max_smem_optin / 6;
+  const bool crowded = K::warp_smem_bytes(a.T, true, a.adj != 0) > (size_t)max_smem_optin / 6;
   if (smem > (size_t)max_smem_optin || (crowded && have_ws && a.do_rollout)) {
     a.k_in_smem = 0;
-    smem = (size_t)nwc * K::warp_smem_bytes(a.T, false);
+    smem = (size_t)nwc * K::warp_smem_bytes(a.T, false, a.adj != 0);
     if (smem > (size_t)max_smem_optin) return 4;
     if (a.do_rollout && !have_ws) return 4;
   }
@@ -875,6 +992,14 @@ int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t str
     kern<<<grid, threads, smem, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : 5;
   };
+  if constexpr (MODE == MODE_MASK) {
+    if (a.adj) {                 // fused KKT adjoint: self-feeding variant only (+ the d tau store)
+      if (prod) return -1;
+      return a.k_in_smem ? go(lqr_step2_kernel<R, N, M, MODE, true, false, true>)
+                         : go(lqr_step2_kernel<R, N, M, MODE, false, false, true>);
+    }
+  }
+  if (a.adj) return -1;
   if (a.k_in_smem) return prod ? go(lqr_step2_kernel<R, N, M, MODE, true, true>) : go(lqr_step2_kernel<R, N, M, MODE, true, false>);
   return prod ? go(lqr_step2_kernel<R, N, M, MODE, false, true>) : go(lqr_step2_kernel<R, N, M, MODE, false, false>);
 }
