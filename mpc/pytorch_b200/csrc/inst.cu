@@ -17,10 +17,10 @@ namespace mpcb200 {
 // a.impl: 0 = pick (the column-pair kernel where its shape constraints hold), 1 = generic kernel, 2 = pair kernel
 template <typename R>
 static int step_dispatch(const StepArgs& a, int max_smem, cudaStream_t s) {
-  if (a.impl == 2 || a.impl == 3 || (a.impl == 0 && Step2Cfg<R, INST_N, INST_M>::PAIR_DEFAULT)) {
+  if (a.impl == 2 || (a.impl == 0 && Step2Cfg<R, INST_N, INST_M>::PAIR_DEFAULT)) {
     const int rc = launch_step2<R, INST_N, INST_M>(a, max_smem, s);
     if (rc >= 0 && !(rc == 4 && a.impl == 0)) return rc;      // rc < 0: shape not supported by the pair mapping
-    if ((a.impl == 2 || a.impl == 3) && rc < 0) return 3;   // MPCB200_ERR_UNSUPPORTED_DIMS
+    if (a.impl == 2 && rc < 0) return 3;   // MPCB200_ERR_UNSUPPORTED_DIMS
   }
   return launch_step<R, INST_N, INST_M>(a, max_smem, s);
 }

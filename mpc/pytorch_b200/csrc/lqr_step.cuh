@@ -53,7 +53,7 @@ struct StepArgs {
   void *Ks, *ks;
   int bulk_ok;    // host-verified: all tensor bases and per-time-step strides are 16-byte aligned
   int k_in_smem;  // gains of all T steps fit in shared memory
-  int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh), 3 pair + producer warp
+  int impl;       // 0 pick, 1 generic (column per lane), 2 column-pair kernel (lqr_step2.cuh)
   long long C_ts, c_ts, F_ts, f_ts;   // elements between consecutive time slices of C, c, F, f (0 = time invariant)
   // fused KKT adjoint (column-pair kernel only): after the masked solve, a third sweep computes the costates and
   // writes dC, dc, dF, df, dx_init; `c` carries -r, the x_bar/u_bar tile slots carry the forward solution tau*

@@ -104,7 +104,6 @@ struct Step2Cfg {
   static constexpr int NXL = N / 2;          // x lanes (own two state columns each)
   static constexpr int PPW = L > 0 ? 32 / (L > 0 ? L : 1) : 1;   // problems per warp
   static constexpr int NW = MPCB2_NW;        // independent (self-feeding) warps per CTA
-  static constexpr int NWC_PROD = 2;         // consumer warps per CTA in the producer variant (+ 1 producer warp)
   static constexpr int EA = 16 / (int)sizeof(R);
   static constexpr int SZ = (int)sizeof(R);
   // shapes this mapping supports: even n, m; per-warp spans of C and F 16-byte multiples (always true for even
@@ -116,7 +115,6 @@ struct Step2Cfg {
   // 1.5-1.8x at n=16, m=4) and for narrow problems (n+m <= 6, where 10+ problems share a warp); in between
   // (n=8, m=2: 39 vs 37 us at config 3) the step is latency bound either way and the generic kernel stays.
   static constexpr bool PAIR_DEFAULT = OK && (P >= 18 || P <= 6 || (N == 8 && M == 4));
-  static constexpr bool PRODUCER_DEFAULT = false;   // a.impl == 3 selects the producer-warp variant
   // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + PPW * P * P;
@@ -255,66 +253,29 @@ MPCB_DEV TileSrc tile_src(const StepArgs& a, int b0, int cnt, unsigned char* wba
   return ts;
 }
 
-template <typename R, int N, int M, int MODE, bool KSM, bool PROD, bool ADJ = false>
-__global__ void __launch_bounds__(PROD ? (Step2Cfg<R, N, M>::NWC_PROD + 1) * 32 : Step2Cfg<R, N, M>::NW * 32)
-    __maxnreg__((Step2Cfg<R, N, M>::MAX_REGS))
+template <typename R, int N, int M, int MODE, bool KSM, bool ADJ = false>
+__global__ void __launch_bounds__(Step2Cfg<R, N, M>::NW * 32) __maxnreg__((Step2Cfg<R, N, M>::MAX_REGS))
 lqr_step2_kernel(const StepArgs a) {
   using K = Step2Cfg<R, N, M>;
   constexpr int P = K::P, L = K::L, NXL = K::NXL, PPW = K::PPW, S = K::S, SZ = K::SZ, KT = K::KT, VSTR = K::VSTR, NV = K::NV;
   constexpr int EA = K::EA, A_N = K::A_N, A_M = K::A_M;
-  constexpr int NWC = PROD ? K::NWC_PROD : K::NW;            // consumer warps per CTA
+  constexpr int NWC = K::NW;                                // independent warps per CTA
   constexpr unsigned FULLM = (1u << M) - 1u;
   constexpr bool BOX = MODE == MODE_BOX;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = (NWC == 1 && !PROD) ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int warp = NWC == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int T = a.T, B = a.B;
   const int has_tb = (BOX && a.bounds_kind == 2) ? 1 : 0;
   // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
   const int G = T + (a.do_rollout ? T : 0);
   const size_t wsm = K::warp_smem_bytes(T, KSM, ADJ);
 
-  if constexpr (PROD) {
-    // ---------------------------------------------------------------- producer variant
-    // NWC consumer warps + ONE producer warp per CTA.  The ~40 uniform-datapath instructions of a tile issue
-    // (360 cycles per step, measured) leave the consumers' dependent chain; a consumer only arrives on the
-    // stage's `empty` mbarrier when it is done reading it.
-    if (warp < NWC && lane == 0) {
-      uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * wsm);
-#pragma unroll
-      for (int s2 = 0; s2 < 2 * S; ++s2) mbar_init(&bars[s2], 1);      // full[S], empty[S]
-      mbar_fence_init();
-    }
-    __syncthreads();
-    if (warp == NWC) {
-      TileSrc ts[NWC];
-      bool live[NWC];
-#pragma unroll
-      for (int w = 0; w < NWC; ++w) {
-        const int b0w = (blockIdx.x * NWC + w) * PPW;
-        live[w] = b0w < B;
-        ts[w] = tile_src<R, N, M>(a, live[w] ? b0w : 0, live[w] ? min(PPW, B - b0w) : 0, smem_raw + (size_t)w * wsm);
-      }
-      int s2 = 0;
-      uint32_t eph = 1u;                                      // parity of the previous use of the stage
-      for (int g = 0; g < G; ++g) {
-#pragma unroll
-        for (int w = 0; w < NWC; ++w) {
-          if (!live[w]) continue;
-          if (g >= S) mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + (size_t)w * wsm) + S + s2, eph);
-          tile_issue<R, N, M>(ts[w], a, s2, g < T ? T - 1 - g : g - T, g >= T, has_tb);
-        }
-        if (++s2 == S) { s2 = 0; eph ^= 1u; }
-      }
-      return;
-    }
-  }
-  const int gw = blockIdx.x * NWC + warp;                   // global (consumer) warp index
+  const int gw = blockIdx.x * NWC + warp;                   // global warp index
   const int b0 = gw * PPW;
-  if (b0 >= B) return;                                      // consumer warps are independent of each other
+  if (b0 >= B) return;                                      // warps are independent: no CTA-wide barrier below
   const int cnt = min(PPW, B - b0);
   unsigned char* wbase = smem_raw + (size_t)warp * wsm;
   uint64_t* full = reinterpret_cast<uint64_t*>(wbase);
-  uint64_t* empty = full + S;                               // used by the producer variant only
   unsigned char* stage_base = wbase + K::HDR_BYTES;
   R* scratch = reinterpret_cast<R*>(stage_base + (size_t)S * K::STAGE_BYTES);
   R* kstore = scratch + (size_t)PPW * K::SCRS;
@@ -339,30 +300,25 @@ lqr_step2_kernel(const StepArgs a) {
   // the load/store scoreboards (global loads that are prefetched across loop iterations end up sharing a
   // scoreboard with the mbarrier probe and expose the full DRAM latency every step - measured).
   const TileSrc tsrc = tile_src<R, N, M>(a, b0, cnt, wbase);
-  if constexpr (!PROD) {
-    if (lane == 0) {
+  if (lane == 0) {
 #pragma unroll
-      for (int s2 = 0; s2 < S; ++s2) mbar_init(&full[s2], 1);
-      mbar_fence_init();
-    }
-    __syncwarp();
+    for (int s2 = 0; s2 < S; ++s2) mbar_init(&full[s2], 1);
+    mbar_fence_init();
   }
-  int iss_s = PROD ? G % S : 0;                             // stage of the next tile this warp issues itself
+  __syncwarp();
+  int iss_s = 0;                                            // stage of the next tile to issue
   auto issue = [&](int t, bool fwd) {
     tile_issue<R, N, M>(tsrc, a, iss_s, t, fwd, has_tb);
     iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
   };
-  // "done with the stage of tile g": self-feeding warps refill it with tile g + S, the producer variant
-  // tells the producer (one lane arrives on the stage's empty barrier)
+  // "done with the stage of tile g": refill it with tile g + S of the global sequence.  (A variant with a
+  // dedicated producer warp per two consumer warps - the consumer only arrives on an `empty` mbarrier - was
+  // measured SLOWER: 43.1 vs 39.0 us at config 3, profiles/r02_step2_producer_variant.log; removed.)
   auto release = [&](int g) {
-    if constexpr (PROD) {
-      if (lane == 0) mbar_arrive(&empty[g % S]);
-    } else {
-      const int gn = g + S;
-      if (gn < G) {
-        if (gn < T) issue(T - 1 - gn, false);
-        else issue(gn - T, true);
-      }
+    const int gn = g + S;
+    if (gn < G) {
+      if (gn < T) issue(T - 1 - gn, false);
+      else issue(gn - T, true);
     }
   };
   int con_s = 0;                                            // stage / phase parity of the next tile to consume
@@ -375,9 +331,7 @@ lqr_step2_kernel(const StepArgs a) {
     if (++con_s == S) { con_s = 0; con_ph ^= 1u; }
     return st;
   };
-  if constexpr (!PROD) {
-    for (int g = 0; g < S && g < G; ++g) release(g - S);     // prologue: tiles 0 .. S-1
-  }
+  for (int g = 0; g < S && g < G; ++g) release(g - S);       // prologue: tiles 0 .. S-1
 
   const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
   auto mask_bits = [&](int t) -> unsigned {               // u_zero_I of (t, problem): M bytes, straight from global
@@ -971,37 +925,31 @@ template <typename R, int N, int M, int MODE>
 int launch_step2_mode(const StepArgs& args, int max_smem_optin, cudaStream_t stream) {
   using K = Step2Cfg<R, N, M>;
   StepArgs a = args;
-  const bool prod = !a.adj && (a.impl == 3 || (a.impl != 2 && K::PRODUCER_DEFAULT));
-  const int nwc = prod ? K::NWC_PROD : K::NW;
+  const bool adj = a.adj != 0;
+  if (adj && MODE != MODE_MASK) return -1;
   a.k_in_smem = 1;
-  size_t smem = (size_t)nwc * K::warp_smem_bytes(a.T, true, a.adj != 0);
+  size_t smem = (size_t)K::NW * K::warp_smem_bytes(a.T, true, adj);
   const bool have_ws = a.Ks != nullptr && a.ks != nullptr;
   // keep a few warps per SM resident: move the gain store to the caller's buffer when it is what limits them
-  const bool crowded = K::warp_smem_bytes(a.T, true, a.adj != 0) > (size_t)max_smem_optin / 6;
+  const bool crowded = K::warp_smem_bytes(a.T, true, adj) > (size_t)max_smem_optin / 6;
   if (smem > (size_t)max_smem_optin || (crowded && have_ws && a.do_rollout)) {
     a.k_in_smem = 0;
-    smem = (size_t)nwc * K::warp_smem_bytes(a.T, false, a.adj != 0);
+    smem = (size_t)K::NW * K::warp_smem_bytes(a.T, false, adj);
     if (smem > (size_t)max_smem_optin) return 4;
     if (a.do_rollout && !have_ws) return 4;
   }
   const int warps = (a.B + K::PPW - 1) / K::PPW;
-  const int grid = (warps + nwc - 1) / nwc;
-  const int threads = prod ? (nwc + 1) * 32 : nwc * 32;
+  const int grid = (warps + K::NW - 1) / K::NW;
   auto go = [&](auto kern) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) return 5;
-    kern<<<grid, threads, smem, stream>>>(a);
+    kern<<<grid, K::NW * 32, smem, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : 5;
   };
   if constexpr (MODE == MODE_MASK) {
-    if (a.adj) {                 // fused KKT adjoint: self-feeding variant only (+ the d tau store)
-      if (prod) return -1;
-      return a.k_in_smem ? go(lqr_step2_kernel<R, N, M, MODE, true, false, true>)
-                         : go(lqr_step2_kernel<R, N, M, MODE, false, false, true>);
-    }
+    if (adj)                     // fused KKT adjoint (+ the d tau store)
+      return a.k_in_smem ? go(lqr_step2_kernel<R, N, M, MODE, true, true>) : go(lqr_step2_kernel<R, N, M, MODE, false, true>);
   }
-  if (a.adj) return -1;
-  if (a.k_in_smem) return prod ? go(lqr_step2_kernel<R, N, M, MODE, true, true>) : go(lqr_step2_kernel<R, N, M, MODE, true, false>);
-  return prod ? go(lqr_step2_kernel<R, N, M, MODE, false, true>) : go(lqr_step2_kernel<R, N, M, MODE, false, false>);
+  return a.k_in_smem ? go(lqr_step2_kernel<R, N, M, MODE, true>) : go(lqr_step2_kernel<R, N, M, MODE, false>);
 }
 
 template <typename R, int N, int M>
