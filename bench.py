@@ -168,8 +168,7 @@ class RawStepper:
 
 
 class RawAdjoint:
-    """Pre-bound one-call KKT adjoint (mpcb200_lqr_adjoint_f32): prep + nested masked step + costates + outer
-    products = 4 kernel launches per call, the C-ABI view of LQRStepFn.backward."""
+    """Pre-bound one-call KKT adjoint (mpcb200_lqr_adjoint_f32), the C-ABI view of LQRStepFn.backward."""
 
     def __init__(self, inp, new_x, new_u, B, T, n, m):
         from mpc.pytorch_b200 import _lib
@@ -350,11 +349,14 @@ def extras(dev, stream, sh, peak):
                                   "kernels_per_backward": int(n_kernels),
                                   "api": "torch.autograd.grad through LQRStep(no_op_forward=True)(...): the autograd engine + LQRStepFn.backward (Python host path included)"}
     raws = [RawAdjoint(s, s["cur_x"], s["cur_u"], 4096, 20, 8, 2) for s in sets3]
+    l0 = _lib.launch_count()
+    raws[0](sh)
+    n_raw = _lib.launch_count() - l0
     us = time_launches(raws, 20, stream, sh)
     res["adjoint_config3_c_abi"] = {"us_per_backward": round(us, 2), "solves_per_s": 4096 / (us * 1e-6),
                                     "bytes_per_solve": ab, "hbm_frac": ab * 4096 / (us * 1e-6) / 1e9 / peak,
-                                    "kernels_per_backward": 4,
-                                    "api": "mpcb200_lqr_adjoint_f32 (prep + masked step + costates + outer products), device resident"}
+                                    "kernels_per_backward": int(n_raw),
+                                    "api": "mpcb200_lqr_adjoint_f32 (prep + fused solve / costate / outer-product kernel), device resident"}
     del raws
     del sets3, sets4, lv
     torch.cuda.empty_cache()
