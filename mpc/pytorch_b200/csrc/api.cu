@@ -198,7 +198,7 @@ static int grad_impl(const mpcb200_dims* d, const R* C, const R* c, const R* F, 
 // KKT adjoint in one call (reference LQRStepFn.backward, mpc/lqr_step.py:312-407)
 // ---------------------------------------------------------------------------------------------
 struct AdjLayout {                    // workspace carve-up (byte offsets, every piece 256-byte aligned)
-  size_t negr, zeros, dx, du, costate, scal, mask, total;
+  size_t negr, zeros, dx, du, costate, scal, mask, maskf, total;
 };
 static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 static AdjLayout adj_layout(int B, int T, int n, int m, size_t sz) {
@@ -212,6 +212,7 @@ static AdjLayout adj_layout(int B, int T, int n, int m, size_t sz) {
   l.costate = o; o += up256(2 * TB * n * sz);
   l.scal = o;    o += up256((size_t)3 * B * sz);
   l.mask = o;    o += up256(TB * m);
+  l.maskf = o;   o += up256(TB * m * sz);                               // the same mask as element-typed 0/1 (rides on the TMA tile)
   l.total = o;
   return l;
 }
@@ -220,7 +221,8 @@ template <typename R>
 __global__ void __launch_bounds__(256)
 adjoint_prep_kernel(int B, int T, int n, int m, int bounds_kind, R s_lo, R s_hi, const R* __restrict__ dl_dx,
                     const R* __restrict__ dl_du, const R* __restrict__ new_u, const R* __restrict__ u_lower,
-                    const R* __restrict__ u_upper, R* __restrict__ negr, unsigned char* __restrict__ mask) {
+                    const R* __restrict__ u_upper, R* __restrict__ negr, unsigned char* __restrict__ mask,
+                    R* __restrict__ maskf) {
   const size_t tb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tb >= (size_t)T * B) return;
   const int p = n + m;
@@ -235,6 +237,7 @@ adjoint_prep_kernel(int B, int T, int n, int m, int bounds_kind, R s_lo, R s_hi,
       on = (fabs(u - lo) <= R(1e-8)) || (fabs(u - hi) <= R(1e-8));
     }
     mask[tb * m + q] = on;
+    maskf[tb * m + q] = on ? R(1) : R(0);
   }
 }
 
@@ -268,7 +271,8 @@ static int adjoint_impl(const mpcb200_dims* d, const mpcb200_params* p, const R*
   R* z0 = zu + TB * d->m;
   if (cudaMemsetAsync(z0, 0, (size_t)d->B * d->n * sizeof(R), st) != cudaSuccess) return MPCB200_ERR_LAUNCH;
   adjoint_prep_kernel<R><<<(unsigned)((TB + 255) / 256), 256, 0, st>>>(
-      d->B, d->T, d->n, d->m, d->bounds_kind, (R)p->u_lo, (R)p->u_hi, dl_dx, dl_du, new_u, u_lower, u_upper, negr, mask);
+      d->B, d->T, d->n, d->m, d->bounds_kind, (R)p->u_lo, (R)p->u_hi, dl_dx, dl_du, new_u, u_lower, u_upper, negr, mask,
+      (R*)(ws + l.maskf));
   if (cudaGetLastError() != cudaSuccess) return MPCB200_ERR_LAUNCH;
   g_launches.fetch_add(1);
   // nested masked LQR step from the zero trajectory (reference :328-340: MPC(lqr_iter=1, u_zero_I=I) with its defaults)
@@ -287,7 +291,8 @@ static int adjoint_impl(const mpcb200_dims* d, const mpcb200_params* p, const R*
     ax.dx_init = dx_init; ax.has_df = d->has_f ? 1 : 0;
     ax.c_ts = tstride(d->c_tstride, (long long)d->B * (d->n + d->m));
     ax.ok = aligned16(c) && aligned16(new_x) && aligned16(new_u) && (ax.c_ts * (long long)sizeof(R)) % 16 == 0;
-    rc = step_impl<R>(&ds, &ps, C, negr, F, (const R*)nullptr, z0, zx, zu, (const R*)nullptr, (const R*)nullptr, mask,
+    const R* maskf = (const R*)(ws + l.maskf);
+    rc = step_impl<R>(&ds, &ps, C, negr, F, (const R*)nullptr, z0, zx, zu, maskf, maskf, mask,
                       dxs, dus, scal, scal + d->B, scal + 2 * d->B, (R*)nullptr, (int32_t*)nullptr,
                       (uint8_t*)nullptr, (int32_t*)nullptr, (R*)nullptr, (R*)nullptr, stream, &ax);
     if (rc == 0) return 0;

@@ -116,9 +116,22 @@ struct Step2Cfg {
   // (n=8, m=2: 39 vs 37 us at config 3) the step is latency bound either way and the generic kernel stays.
   static constexpr bool PAIR_DEFAULT = OK && (P >= 18 || P <= 6 || (N == 8 && M == 4));
   // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
+  // Per-problem strides of the C and F tiles inside a stage.  The problems of a warp read the same tile offsets at
+  // the same time; when the dense stride is a multiple of 16 words they hit the same banks (n=16, m=4: F tiles
+  // 320 floats apart -> every broadcast load of F is a 3-way conflict; ncu: 38 % of all shared wavefronts).  Big
+  // tiles are therefore copied per problem with a stride that is 4 mod 8 words; small tiles (where the extra bulk
+  // copies would sit on the step's critical path) keep the dense layout and one copy per tensor.
+  static constexpr bool PADDED = P >= 18;
+  static constexpr int pad_stride(int dense) {
+    if (!PADDED) return dense;
+    int st = dense;
+    while (st % 8 != 4) st += 4;
+    return st;
+  }
+  static constexpr int CS = pad_stride(P * P), FS = pad_stride(N * P);
   static constexpr int OFF_C = 0;
-  static constexpr int OFF_F = OFF_C + PPW * P * P;
-  static constexpr int OFF_c = OFF_F + PPW * N * P;
+  static constexpr int OFF_F = OFF_C + PPW * CS;
+  static constexpr int OFF_c = OFF_F + PPW * FS;
   static constexpr int OFF_x = OFF_c + PPW * P;
   static constexpr int OFF_u = OFF_x + PPW * N;
   static constexpr int OFF_f = OFF_u + PPW * M;
@@ -191,15 +204,17 @@ MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t,
   const size_t tB = (size_t)t * a.B * SZ;
   const uint32_t total = ts.ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0) + (a.adj ? P : 0)) +
                          (needF ? ts.ucnt * (N * P) : 0u) + (needf ? ts.ucnt * N : 0u);
+  constexpr int dense = K::PADDED ? 0 : 1;          // dense layout: C and F go as one copy each (first asm block)
   asm volatile(
-      "{\n\t.reg .pred P, PF, Pf, PB;\n\t.reg .b32 d, n;\n\t"
+      "{\n\t.reg .pred P, PF, Pf, PB, PC;\n\t.reg .b32 d, n;\n\t"
       "elect.sync _|P, 0xffffffff;\n\t"
       "setp.ne.and.b32 PF, %12, 0, P;\n\t"
       "setp.ne.and.b32 Pf, %13, 0, P;\n\t"
       "setp.ne.and.b32 PB, %14, 0, P;\n\t"
+      "setp.ne.and.b32 PC, %27, 0, P;\n\t"
       "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
       "mul.lo.u32 n, %3, %15;\n\t"
-      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
+      "@PC cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
       "mul.lo.u32 n, %3, %16;\n\tadd.u32 d, %2, %17;\n\t"
       "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%5], n, [%0];\n\t"
       "mul.lo.u32 n, %3, %18;\n\tadd.u32 d, %2, %19;\n\t"
@@ -218,10 +233,28 @@ MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t,
       "l"(ts.pC + (size_t)t * a.C_ts * SZ), "l"(ts.pF + (size_t)t * a.F_ts * SZ),                             // 4 5
       "l"(ts.pc + (size_t)t * a.c_ts * SZ), "l"(ts.px + tB * N),                                               // 6 7
       "l"(ts.pu + tB * M), "l"(ts.pf + (size_t)t * a.f_ts * SZ), "l"(ts.plo + tB * M), "l"(ts.phi + tB * M),  // 8..11
-      "r"(needF), "r"(needf), "r"(has_tb),                                                                     // 12 13 14
+      "r"(needF & dense), "r"(needf), "r"(has_tb),                                                             // 12 13 14
       "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),      // 15..21
-      "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)                 // 22..26
+      "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ),                // 22..26
+      "r"(dense)                                                                                               // 27
       : "memory");
+  if constexpr (K::PADDED) {   // padded layout: one copy per problem for C and F (their bytes are in `total`)
+    const int cnt = (int)(ts.ucnt / SZ);
+    const char* sC = ts.pC + (size_t)t * a.C_ts * SZ;
+    const char* sF = ts.pF + (size_t)t * a.F_ts * SZ;
+    for (int q = 0; q < cnt; ++q) {
+      asm volatile(
+          "{\n\t.reg .pred P, PF;\n\t"
+          "elect.sync _|P, 0xffffffff;\n\t"
+          "setp.ne.and.b32 PF, %7, 0, P;\n\t"
+          "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t"
+          "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%5], %6, [%0];\n\t"
+          "}" ::"r"(bar), "r"(dst + (uint32_t)(K::OFF_C + q * K::CS) * SZ), "l"(sC + (size_t)q * (P * P) * SZ),
+          "r"((uint32_t)(P * P) * SZ), "r"(dst + (uint32_t)(K::OFF_F + q * K::FS) * SZ),
+          "l"(sF + (size_t)q * (N * P) * SZ), "r"((uint32_t)(N * P) * SZ), "r"(needF)
+          : "memory");
+    }
+  }
   if (a.adj) {      // fused adjoint: the true cost's c rides on the same mbarrier (its bytes are in `total`)
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
@@ -265,7 +298,8 @@ lqr_step2_kernel(const StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = NWC == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int T = a.T, B = a.B;
-  const int has_tb = (BOX && a.bounds_kind == 2) ? 1 : 0;
+  // tensor bounds ride in the lo/hi slots; the fused adjoint uses the lo slot for its active-set mask (as R values)
+  const int has_tb = (ADJ || (BOX && a.bounds_kind == 2)) ? 1 : 0;
   // global tile sequence of the sweep + first rollout pass: g < T -> t = T-1-g (backward), else t = g-T (forward)
   const int G = T + (a.do_rollout ? T : 0);
   const size_t wsm = K::warp_smem_bytes(T, KSM, ADJ);
@@ -334,9 +368,13 @@ lqr_step2_kernel(const StepArgs a) {
   for (int g = 0; g < S && g < G; ++g) release(g - S);       // prologue: tiles 0 .. S-1
 
   const bool has_mask = MODE == MODE_MASK || (BOX && a.has_mask);
-  auto mask_bits = [&](int t) -> unsigned {               // u_zero_I of (t, problem): M bytes, straight from global
+  const int olo_ = K::OFF_lo + pi * M;
+  auto mask_bits = [&](int t, const R* stt) -> unsigned {  // u_zero_I of (t, problem)
     unsigned z = 0u;
-    if (has_mask) {
+    if constexpr (ADJ) {                                   // fused adjoint: on the tile (no global load on the chain)
+#pragma unroll
+      for (int q = 0; q < M; ++q) z |= (stt[olo_ + q] != R(0) ? 1u : 0u) << q;
+    } else if (has_mask) {                                 // M bytes straight from global
 #pragma unroll
       for (int q = 0; q < M; ++q) z |= (a.zero_mask[((size_t)t * B + bsafe) * M + q] ? 1u : 0u) << q;
     }
@@ -344,7 +382,7 @@ lqr_step2_kernel(const StepArgs a) {
   };
 
   // per-problem element offsets inside a stage
-  const int oC = K::OFF_C + pi * P * P, oF = K::OFF_F + pi * N * P;
+  const int oC = K::OFF_C + pi * K::CS, oF = K::OFF_F + pi * K::FS;
   const int oc = K::OFF_c + pi * P, of_ = K::OFF_f + pi * N, ox = K::OFF_x + pi * N, ou = K::OFF_u + pi * M;
   const int olo = K::OFF_lo + pi * M, ohi = K::OFF_hi + pi * M;
   R* scr = scratch + (size_t)pi * K::SCRS;
@@ -412,7 +450,7 @@ lqr_step2_kernel(const StepArgs a) {
         bhi[q] = stt[ohi + q];
       }
     }
-    zmk = mask_bits(tt);
+    zmk = mask_bits(tt, stt);
   };
   const R* st = acquire(0u);
   pre(T - 1, st);
@@ -708,7 +746,7 @@ lqr_step2_kernel(const StepArgs a) {
           hi_t[q] = stt[ohi + q];
         }
       }
-      zm = mask_bits(tt);
+      zm = mask_bits(tt, stt);
     };
     st = acquire(0u);
     load_gain(0);
