@@ -116,19 +116,11 @@ struct Step2Cfg {
   // (n=8, m=2: 39 vs 37 us at config 3) the step is latency bound either way and the generic kernel stays.
   static constexpr bool PAIR_DEFAULT = OK && (P >= 18 || P <= 6 || (N == 8 && M == 4));
   // stage layout (elements): dense spans of the warp's PPW problems, in the tensors' own layouts
-  // Per-problem strides of the C and F tiles inside a stage.  The problems of a warp read the same tile offsets at
-  // the same time; when the dense stride is a multiple of 16 words they hit the same banks (n=16, m=4: F tiles
-  // 320 floats apart -> every broadcast load of F is a 3-way conflict; ncu: 38 % of all shared wavefronts).  Big
-  // tiles are therefore copied per problem with a stride that is 4 mod 8 words; small tiles (where the extra bulk
-  // copies would sit on the step's critical path) keep the dense layout and one copy per tensor.
-  static constexpr bool PADDED = P >= 18;
-  static constexpr int pad_stride(int dense) {
-    if (!PADDED) return dense;
-    int st = dense;
-    while (st % 8 != 4) st += 4;
-    return st;
-  }
-  static constexpr int CS = pad_stride(P * P), FS = pad_stride(N * P);
+  // Per-problem tiles are dense (stride p*p / n*p).  Padding them per problem to dodge the bank conflicts of the
+  // broadcast loads (n=16, m=4: F tiles 320 floats apart, 38 % of the shared wavefronts are conflicts) was
+  // measured: 449 vs 447 us at B=4096, 1504 vs 1457 us at B=16384 - the extra per-problem bulk copies cost what
+  // the conflicts did (profiles/r02_config5_padded_tiles_experiment.log); removed.
+  static constexpr int CS = P * P, FS = N * P;
   static constexpr int OFF_C = 0;
   static constexpr int OFF_F = OFF_C + PPW * CS;
   static constexpr int OFF_c = OFF_F + PPW * FS;
@@ -204,17 +196,15 @@ MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t,
   const size_t tB = (size_t)t * a.B * SZ;
   const uint32_t total = ts.ucnt * (P * P + P + N + M + (has_tb ? 2 * M : 0) + (a.adj ? P : 0)) +
                          (needF ? ts.ucnt * (N * P) : 0u) + (needf ? ts.ucnt * N : 0u);
-  constexpr int dense = K::PADDED ? 0 : 1;          // dense layout: C and F go as one copy each (first asm block)
   asm volatile(
-      "{\n\t.reg .pred P, PF, Pf, PB, PC;\n\t.reg .b32 d, n;\n\t"
+      "{\n\t.reg .pred P, PF, Pf, PB;\n\t.reg .b32 d, n;\n\t"
       "elect.sync _|P, 0xffffffff;\n\t"
       "setp.ne.and.b32 PF, %12, 0, P;\n\t"
       "setp.ne.and.b32 Pf, %13, 0, P;\n\t"
       "setp.ne.and.b32 PB, %14, 0, P;\n\t"
-      "setp.ne.and.b32 PC, %27, 0, P;\n\t"
       "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
       "mul.lo.u32 n, %3, %15;\n\t"
-      "@PC cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
+      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%4], n, [%0];\n\t"
       "mul.lo.u32 n, %3, %16;\n\tadd.u32 d, %2, %17;\n\t"
       "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d], [%5], n, [%0];\n\t"
       "mul.lo.u32 n, %3, %18;\n\tadd.u32 d, %2, %19;\n\t"
@@ -233,28 +223,10 @@ MPCB_DEV void tile_issue(const TileSrc& ts, const StepArgs& a, int stage, int t,
       "l"(ts.pC + (size_t)t * a.C_ts * SZ), "l"(ts.pF + (size_t)t * a.F_ts * SZ),                             // 4 5
       "l"(ts.pc + (size_t)t * a.c_ts * SZ), "l"(ts.px + tB * N),                                               // 6 7
       "l"(ts.pu + tB * M), "l"(ts.pf + (size_t)t * a.f_ts * SZ), "l"(ts.plo + tB * M), "l"(ts.phi + tB * M),  // 8..11
-      "r"(needF & dense), "r"(needf), "r"(has_tb),                                                             // 12 13 14
+      "r"(needF), "r"(needf), "r"(has_tb),                                                                      // 12 13 14
       "n"(P * P), "n"(N * P), "n"(K::OFF_F * SZ), "n"(P), "n"(K::OFF_c * SZ), "n"(N), "n"(K::OFF_x * SZ),      // 15..21
-      "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ),                // 22..26
-      "r"(dense)                                                                                               // 27
+      "n"(M), "n"(K::OFF_f * SZ), "n"(K::OFF_u * SZ), "n"(K::OFF_lo * SZ), "n"(K::OFF_hi * SZ)                 // 22..26
       : "memory");
-  if constexpr (K::PADDED) {   // padded layout: one copy per problem for C and F (their bytes are in `total`)
-    const int cnt = (int)(ts.ucnt / SZ);
-    const char* sC = ts.pC + (size_t)t * a.C_ts * SZ;
-    const char* sF = ts.pF + (size_t)t * a.F_ts * SZ;
-    for (int q = 0; q < cnt; ++q) {
-      asm volatile(
-          "{\n\t.reg .pred P, PF;\n\t"
-          "elect.sync _|P, 0xffffffff;\n\t"
-          "setp.ne.and.b32 PF, %7, 0, P;\n\t"
-          "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t"
-          "@PF cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%5], %6, [%0];\n\t"
-          "}" ::"r"(bar), "r"(dst + (uint32_t)(K::OFF_C + q * K::CS) * SZ), "l"(sC + (size_t)q * (P * P) * SZ),
-          "r"((uint32_t)(P * P) * SZ), "r"(dst + (uint32_t)(K::OFF_F + q * K::FS) * SZ),
-          "l"(sF + (size_t)q * (N * P) * SZ), "r"((uint32_t)(N * P) * SZ), "r"(needF)
-          : "memory");
-    }
-  }
   if (a.adj) {      // fused adjoint: the true cost's c rides on the same mbarrier (its bytes are in `total`)
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
