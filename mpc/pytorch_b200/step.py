@@ -632,7 +632,11 @@ class LQRStepFn(Function):
             n_qp = float("nan")
         elif o.u_lower is not None:
             # reference: sum_t (1 + i_t) with one batched pnqp per step (:140)
-            n_qp = float((1 + res["qp_iters"].max(dim=1).values).sum().item())
+            per_t = 1 + res["qp_iters"].max(dim=1).values
+            if o.verbose > 1:                                   # reference :138-139, one line per time step
+                for v in reversed(per_t.tolist()):              # the sweep runs t = T-1 .. 0
+                    print("  + n_qp_iter: ", v)
+            n_qp = float(per_t.sum().item())
             if o.verbose >= 0 and bool((res["status"] & 1).any()):
                 print("[WARNING] pnqp warning: Did not converge")   # reference pnqp.py:81
         else:
