@@ -132,10 +132,13 @@ struct Step2Cfg {
   static constexpr int OFF_c2 = OFF_hi + PPW * M;        // fused adjoint: the true cost's c (the c slot carries -r)
   static constexpr int OFF_END = OFF_c2 + PPW * P;
   static constexpr int STAGE_BYTES = round_up(OFF_END * SZ, 128);
-  // ring depth.  Measured for n=16, m=4 (9.3 KB tiles): 2 stages + a 200-register cap (9 warps / SM instead of 5)
-  // is SLOWER (688 vs 449 us at B=4096, 1953 vs 1463 us at B=16384): the spills and the single tile of
-  // prefetch cost more than the extra resident warps bring.
-  static constexpr int S = MPCB2_STAGES;
+  // ring depth: 4 stages for small tiles, 3 for big ones.  Measured for n=16, m=4 (9.4 KB tiles, B=4096 / 16384,
+  // profiles/r02_config5_stages_experiment.log): 4 stages (5 warps / SM) 447 / 1457 us, 3 stages (6 warps / SM)
+  // 398 / 1399 us, 2 stages (8 warps / SM) 462 / 1422 us, 2 stages + a 200-register cap (spills) 688 / 1953 us.
+#ifndef MPCB2_BIG_STAGES
+#define MPCB2_BIG_STAGES 3
+#endif
+  static constexpr int S = STAGE_BYTES > 6144 ? MPCB2_BIG_STAGES : MPCB2_STAGES;
   static constexpr int MAX_REGS = 255;
   // per-problem scratch (elements)
   static constexpr int NV = round_up(N, 4);             // row stride of V / K rows (16-byte aligned rows)
