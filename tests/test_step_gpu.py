@@ -58,6 +58,13 @@ CASES = [
     ("unb_f64_n6m2_T60", 12, 7, 60, 6, 2, torch.float64, None, None, False, True),
     ("unb_f64_T1", 15, 3, 1, 4, 2, torch.float64, None, None, False, True),
     ("box_f64_T2", 17, 3, 2, 4, 2, torch.float64, 0.2, None, False, True),
+    # shapes / batch sizes that take the column-pair kernel (even n, m; 16-byte aligned spans), every mode
+    ("pair_delta_f64_n4m2", 18, 8, 6, 4, 2, torch.float64, 0.5, 0.1, False, True),
+    ("pair_boxT_f32_n4m2_tail", 19, 44, 9, 4, 2, torch.float32, "tensor", None, True, True),
+    ("pair_delta_f32_n16m4", 20, 8, 7, 16, 4, torch.float32, 0.4, 0.15, False, True),
+    ("pair_unb_f32_n2m2", 21, 20, 5, 2, 2, torch.float32, None, None, True, False),
+    ("pair_box_f64_n8m4", 22, 12, 6, 8, 4, torch.float64, 0.3, None, False, True),
+    ("pair_unb_f64_T1", 23, 4, 1, 4, 2, torch.float64, None, None, False, True),
 ]
 
 
@@ -124,10 +131,11 @@ def test_step_matches_reference_fixture(name):
         assert abs(n_qp - float(g["n_total_qp_iter"])) <= 2          # +-1 noise
 
 
+@pytest.mark.parametrize("B", [9, 16])          # 16: aligned spans -> the column-pair kernel also in float32
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_masked_adjoint_mode_matches_oracle(dtype):
+def test_masked_adjoint_mode_matches_oracle(dtype, B):
     """u_zero_I branch (reference lqr_step.py:100-127,197-198) - the mode the backward pass uses."""
-    B, T, n, m = 9, 7, 4, 2
+    T, n, m = 7, 4, 2
     C, c, F, f, x0 = gen_problem(10, B, T, n, m, dtype)
     g = torch.Generator().manual_seed(3)
     zI = torch.rand(T, B, m, generator=g) < 0.35
