@@ -22,6 +22,17 @@ from ._lib import MpcB200Error, check, ptr, stream_handle
 DYN_LINEAR, DYN_CARTPOLE, DYN_PENDULUM = 0, 1, 2
 
 
+def _host_values(owner, params):
+    """Python floats of a (possibly CUDA, possibly learnable) parameter tensor, read back only when it changed:
+    the kernels take the parameters by value, and a device->host read per kernel call would serialise the GPU."""
+    key = (params.data_ptr(), params._version, params.device)
+    hit = getattr(owner, "_mpcb200_host_cache", None)
+    if hit is None or hit[0] != key:
+        hit = (key, tuple(float(v) for v in params.detach().cpu()))
+        owner._mpcb200_host_cache = hit
+    return hit[1]
+
+
 class CartpoleDx(Module):
     """state = (x, dx, cos th, sin th, dth), one control (force, clamped to +-force_mag), semi-implicit Euler."""
     mpcb200_kind = DYN_CARTPOLE
@@ -43,7 +54,7 @@ class CartpoleDx(Module):
         self.max_linesearch_iter = 2
 
     def mpcb200_params(self):
-        g, mc, mp, l = (float(v) for v in self.params.detach().cpu())
+        g, mc, mp, l = _host_values(self, self.params)
         return (g, mc, mp, l, float(self.force_mag), float(self.dt), 0.0, 0.0)
 
     def forward(self, state, u):
@@ -93,7 +104,7 @@ class PendulumDx(Module):
         self.max_linesearch_iter = 5
 
     def mpcb200_params(self):
-        g, m, l = (float(v) for v in self.params.detach().cpu())
+        g, m, l = _host_values(self, self.params)
         return (g, m, l, 0.0, float(self.max_torque), float(self.dt), 0.0, 0.0)
 
     def forward(self, x, u):
