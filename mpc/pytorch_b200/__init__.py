@@ -8,4 +8,5 @@ libmpcb200.so).  CUDA only; there is no CPU fallback.
 from .solver import MPC, QuadCost, LinDx, GradMethods  # noqa: F401
 from .step import LQRStep, lqr_step_raw, lqr_grad_raw  # noqa: F401
 from .boxqp import pnqp  # noqa: F401
+from .models import NNDynamics, AffineDynamics  # noqa: F401
 from . import _lib  # noqa: F401

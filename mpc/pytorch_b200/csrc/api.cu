@@ -222,10 +222,12 @@ __global__ void __launch_bounds__(256)
 adjoint_prep_kernel(int B, int T, int n, int m, int bounds_kind, R s_lo, R s_hi, const R* __restrict__ dl_dx,
                     const R* __restrict__ dl_du, const R* __restrict__ new_u, const R* __restrict__ u_lower,
                     const R* __restrict__ u_upper, R* __restrict__ negr, unsigned char* __restrict__ mask,
-                    R* __restrict__ maskf) {
+                    R* __restrict__ maskf, R* __restrict__ z0) {
   const size_t tb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tb >= (size_t)T * B) return;
   const int p = n + m;
+  if (tb < (size_t)B)                              // x_init = 0 of the nested solve (saves a memset node)
+    for (int i = 0; i < n; ++i) z0[tb * n + i] = R(0);
   for (int i = 0; i < n; ++i) negr[tb * p + i] = -dl_dx[tb * n + i];
   for (int q = 0; q < m; ++q) {
     negr[tb * p + n + q] = -dl_du[tb * m + q];
@@ -269,10 +271,9 @@ static int adjoint_impl(const mpcb200_dims* d, const mpcb200_params* p, const R*
   R* zx = zeros;
   R* zu = zeros + TB * d->n;
   R* z0 = zu + TB * d->m;
-  if (cudaMemsetAsync(z0, 0, (size_t)d->B * d->n * sizeof(R), st) != cudaSuccess) return MPCB200_ERR_LAUNCH;
   adjoint_prep_kernel<R><<<(unsigned)((TB + 255) / 256), 256, 0, st>>>(
       d->B, d->T, d->n, d->m, d->bounds_kind, (R)p->u_lo, (R)p->u_hi, dl_dx, dl_du, new_u, u_lower, u_upper, negr, mask,
-      (R*)(ws + l.maskf));
+      (R*)(ws + l.maskf), z0);
   if (cudaGetLastError() != cudaSuccess) return MPCB200_ERR_LAUNCH;
   g_launches.fetch_add(1);
   // nested masked LQR step from the zero trajectory (reference :328-340: MPC(lqr_iter=1, u_zero_I=I) with its defaults)

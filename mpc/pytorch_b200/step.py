@@ -379,23 +379,30 @@ def _workspace(nbytes, dev):
     return buf
 
 
-def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper, want_df, f_T=None):
+_adj_plans = {}
+
+
+def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_lower, u_upper, want_df, f_T=None,
+                    validated=False):
     """LQRStepFn.backward in ONE library call (prep + nested masked step + costates + outer products);
     returns (dx_init, dC, dc, dF, df|None), or None when this shape needs the general multi-call path
-    (zero-padded instance, horizon too long for the shared-memory gain store)."""
+    (zero-padded instance, horizon too long for the shared-memory gain store).  `validated`: the tensors are the
+    ones LQRStepFn.forward checked and saved plus autograd's gradients of its outputs (shapes follow), so the
+    shape / device checks are not repeated on the backward path."""
     dtype, dev = C.dtype, C.device
     n, m = n_state, n_ctrl
     if _pick_instance(n, m) != (n, m) or _is_empty(F):
         return None
     B = C.shape[1]
     p = n + m
-    _expect("C", C, (T, B, p, p), dev)
-    _expect("c", c, (T, B, p), dev)
-    _expect("F", F, (F.shape[0], B, n, p), dev)
-    for nm, t_, sh in (("new_x", new_x, (T, B, n)), ("new_u", new_u, (T, B, m)), ("dl_dx", dl_dx, (T, B, n)),
-                       ("dl_du", dl_du, (T, B, m))):
-        _expect(nm, t_, sh, dev)
     F_T = F.shape[0]
+    if not validated:
+        _expect("C", C, (T, B, p, p), dev)
+        _expect("c", c, (T, B, p), dev)
+        _expect("F", F, (F_T, B, n, p), dev)
+        for nm, t_, sh in (("new_x", new_x, (T, B, n)), ("new_u", new_u, (T, B, m)), ("dl_dx", dl_dx, (T, B, n)),
+                           ("dl_du", dl_du, (T, B, m))):
+            _expect(nm, t_, sh, dev)
     kind, s_lo, s_hi, lo_t, hi_t = 0, 0.0, 0.0, None, None
     if u_lower is not None:
         if isinstance(u_lower, float) and isinstance(u_upper, float):
@@ -408,19 +415,25 @@ def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_l
                     else _dense(u_upper, dtype))
             _expect("u_lower", lo_t, (T, B, m), dev)
             _expect("u_upper", hi_t, (T, B, m), dev)
-    dims = Dims(B=B, T=T, n=n, m=m, F_T=F_T, has_f=int(want_df), bounds_kind=kind, has_zero_mask=0,
-                has_delta_u=0, max_ls_iter=10, pnqp_max_iter=PNQP_MAX_ITER, do_rollout=1)
+    (C_, tsC), (c_, tsc), (F_, tsF) = _time_strided(C, dtype), _time_strided(c, dtype), _time_strided(F, dtype)
     L = _lib.lib()
-    key = (n, m, T, C.element_size())
-    fits = _smem_fits_cache.get(key)
-    if fits is None:
-        fits = not L.mpcb200_step_prefers_workspace(ctypes.byref(dims), C.element_size())
-        _smem_fits_cache[key] = fits
+    esz = C.element_size()
+    # the ctypes structs, the shared-memory fit and the workspace size depend only on this key: build them once
+    key = (n, m, T, B, F_T, esz, kind, s_lo, s_hi, bool(want_df), tsC, tsc, tsF)
+    plan = _adj_plans.get(key)
+    if plan is None:
+        dims = Dims(B=B, T=T, n=n, m=m, F_T=F_T, has_f=int(want_df), bounds_kind=kind, has_zero_mask=0,
+                    has_delta_u=0, max_ls_iter=10, pnqp_max_iter=PNQP_MAX_ITER, do_rollout=1,
+                    C_tstride=tsC, c_tstride=tsc, F_tstride=tsF)
+        fits = not L.mpcb200_step_prefers_workspace(ctypes.byref(dims), esz)
+        params = Params(u_lo=float(s_lo), u_hi=float(s_hi), delta_u=0.0, ls_decay=0.2)
+        nbytes = L.mpcb200_adjoint_workspace_bytes(ctypes.byref(dims), esz) if fits else 0
+        if len(_adj_plans) > 256:
+            _adj_plans.clear()
+        plan = _adj_plans[key] = (fits, dims, params, ctypes.byref(dims), ctypes.byref(params), nbytes)
+    fits, dims, params, dims_ref, params_ref, nbytes = plan
     if not fits:
         return None
-    params = Params(u_lo=float(s_lo), u_hi=float(s_hi), delta_u=0.0, ls_decay=0.2)
-    (C_, tsC), (c_, tsc), (F_, tsF) = _time_strided(C, dtype), _time_strided(c, dtype), _time_strided(F, dtype)
-    dims.C_tstride, dims.c_tstride, dims.F_tstride = tsC, tsc, tsF
     nx_, nu_, gx_, gu_ = _dense(new_x, dtype), _dense(new_u, dtype), _dense(dl_dx, dtype), _dense(dl_du, dtype)
     dx_init = torch.empty(B, n, dtype=dtype, device=dev)
     dC = torch.empty(T, B, p, p, dtype=dtype, device=dev)
@@ -430,13 +443,12 @@ def lqr_adjoint_raw(n_state, n_ctrl, T, C, c, F, new_x, new_u, dl_dx, dl_du, u_l
     df = torch.empty(f_T, B, n, dtype=dtype, device=dev) if want_df else None
     if want_df and f_T == T:
         df[T - 1].zero_()
-    nbytes = L.mpcb200_adjoint_workspace_bytes(ctypes.byref(dims), C.element_size())
     ws = _workspace(nbytes, dev)
     fn = L.mpcb200_lqr_adjoint_f32 if dtype == torch.float32 else L.mpcb200_lqr_adjoint_f64
     with _on_device(dev):
-        rc = fn(ctypes.byref(dims), ctypes.byref(params), ptr_view(C_), ptr_view(c_), ptr_view(F_), ptr(nx_), ptr(nu_), ptr(gx_),
+        rc = fn(dims_ref, params_ref, ptr_view(C_), ptr_view(c_), ptr_view(F_), ptr(nx_), ptr(nu_), ptr(gx_),
                 ptr(gu_), ptr(lo_t), ptr(hi_t), ptr(dx_init), ptr(dC), ptr(dc), ptr(dF), ptr(df), ptr(ws),
-                ctypes.c_size_t(nbytes), stream_handle(dev))
+                nbytes, stream_handle(dev))
     check(rc, "mpcb200_lqr_adjoint")
     return dx_init, dC, dc, dF, df
 
@@ -589,6 +601,23 @@ class LQRStepFn(Function):
         from .dynamics import known_kind
         ctx.o = o
         if o.no_op_forward:                                   # reference :278-282
+            # nothing is computed here, but backward hands these tensors to the kernels as raw pointers:
+            # check shapes / devices now, at the call site, once
+            n, m, T = o.n_state, o.n_ctrl, o.T
+            dev, B = C.device, C.shape[1] if C.dim() == 4 else -1
+            _expect("C", C, (T, B, n + m, n + m), dev)
+            _expect("c", c, (T, B, n + m), dev)
+            _expect("x_init", x_init, (B, n), dev)
+            if not _is_empty(F):
+                if F.dim() != 4 or F.shape[0] not in (T - 1, T):
+                    raise MpcB200Error(f"F: expected [T-1|T,B,n,n+m], got {tuple(F.shape)}")
+                _expect("F", F, (F.shape[0], B, n, n + m), dev)
+            if not _is_empty(f):
+                if f.shape[0] not in (T - 1, T):
+                    raise MpcB200Error(f"f: expected [T-1|T,B,n], got {tuple(f.shape)}")
+                _expect("f", f, (f.shape[0], B, n), dev)
+            _expect("current_x", o.current_x, (T, B, n), dev)
+            _expect("current_u", o.current_u, (T, B, m), dev)
             ctx.save_for_backward(x_init, C, c, F, f, o.current_x, o.current_u)
             return o.current_x, o.current_u
         assert o.delta_space                                  # reference :284,298
@@ -655,7 +684,7 @@ class LQRStepFn(Function):
             dl_du = torch.zeros_like(new_u)
         want_df = not _is_empty(f)
         fast = lqr_adjoint_raw(o.n_state, o.n_ctrl, o.T, C, c, F, new_x, new_u, dl_dx, dl_du, o.u_lower, o.u_upper,
-                               want_df, f_T=f.shape[0] if want_df else None)
+                               want_df, f_T=f.shape[0] if want_df else None, validated=True)
         if fast is not None:                                # the whole backward in one library call
             dx_init, dC, dc, dF, df = fast
             if df is None:

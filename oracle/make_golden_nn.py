@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Fixtures for the learned / affine dynamics modules, from the REAL reference.
+
+Run in the build container (where /root/reference exists):   python oracle/make_golden_nn.py
+Imports the unmodified reference under the alias ``ref_mpc`` (oracle/make_golden.py: load_reference), builds its
+``NNDynamics`` / ``AffineDynamics`` (reference mpc/dynamics.py:15-131, :159-205) with seeded weights, and stores the
+weights, one batched step, the analytic Jacobians ``grad_input`` and a short box-constrained iLQR solve with
+``GradMethods.ANALYTIC`` as tests/golden/nn_dynamics_*.npz / affine_dynamics_f64.npz.  Only numbers are stored.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+from make_golden import load_reference, npz          # noqa: E402
+
+
+def main():
+    rmpc, _, _, _ = load_reference()
+    import ref_mpc.dynamics as rdyn
+    torch.set_default_dtype(torch.float64)
+    n, m, B, T = 3, 2, 4, 8
+    p = n + m
+    for act in ("sigmoid", "relu"):
+        torch.manual_seed(7 if act == "sigmoid" else 8)
+        net = rdyn.NNDynamics(n, m, hidden_sizes=[12, 10], activation=act, passthrough=True).double()
+        with torch.no_grad():
+            for fc in net.fcs:                       # O(1) Jacobians so the iLQR problem is non-trivial
+                fc.weight.mul_(1.5)
+        xs, us = torch.randn(9, n), torch.randn(9, m)
+        nxt = net(xs, us)
+        R, S = net.grad_input(xs, us)
+        L = torch.randn(T, B, p, p) / p ** 0.5
+        C = L @ L.transpose(-1, -2) + torch.eye(p)
+        c = 0.5 * torch.randn(T, B, p)
+        x0 = torch.randn(B, n)
+        with contextlib.redirect_stdout(io.StringIO()):
+            x, u, costs = rmpc.MPC(n, m, T, u_lower=-0.6, u_upper=0.6, lqr_iter=12, verbose=-1,
+                                   grad_method=rmpc.GradMethods.ANALYTIC, exit_unconverged=False,
+                                   detach_unconverged=False, eps=1e-6)(x0, rmpc.QuadCost(C, c), net)
+        ws = {f"W{i}": fc.weight for i, fc in enumerate(net.fcs)}
+        ws.update({f"b{i}": fc.bias for i, fc in enumerate(net.fcs)})
+        npz(f"nn_dynamics_{act}_f64", step_x=xs, step_u=us, step_next=nxt, R=R, S=S, C=C, c=c, x_init=x0,
+            x=x, u=u, costs=costs, n_layers=np.int64(len(net.fcs)), **ws)
+        print(act, "clamped fraction", float((u.abs() == 0.6).double().mean()), "cost", float(costs.mean()))
+    # affine dynamics: x' = A x + B u + c (one system shared by the batch)
+    torch.manual_seed(9)
+    A = 0.9 * torch.eye(n) + 0.2 * torch.randn(n, n)
+    Bm = torch.randn(n, m)
+    cc = 0.1 * torch.randn(n)
+    aff = rdyn.AffineDynamics(A, Bm, cc)
+    L = torch.randn(T, B, p, p) / p ** 0.5
+    C = L @ L.transpose(-1, -2) + torch.eye(p)
+    c = 0.5 * torch.randn(T, B, p)
+    x0 = torch.randn(B, n)
+    with contextlib.redirect_stdout(io.StringIO()):
+        x, u, costs = rmpc.MPC(n, m, T, u_lower=-0.5, u_upper=0.5, lqr_iter=12, verbose=-1,
+                               grad_method=rmpc.GradMethods.ANALYTIC, exit_unconverged=False,
+                               detach_unconverged=False, eps=1e-6)(x0, rmpc.QuadCost(C, c), aff)
+    npz("affine_dynamics_f64", A=A, B=Bm, c0=cc, C=C, c=c, x_init=x0, x=x, u=u, costs=costs)
+    print("affine clamped fraction", float((u.abs() == 0.5).double().mean()))
+
+
+if __name__ == "__main__":
+    main()

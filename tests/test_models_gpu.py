@@ -1,0 +1,52 @@
+"""iLQR through learned / affine dynamics with GradMethods.ANALYTIC (grad_input Jacobians, reference
+mpc/mpc.py:495-524) vs trajectories of the unmodified reference (oracle/make_golden_nn.py), float64."""
+import pytest
+import torch
+
+from tests.helpers import load_golden, maxdiff
+from tests.test_models_cpu import build_net
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def solve(g, dx, bound):
+    from mpc.pytorch_b200 import MPC, QuadCost, GradMethods
+    T = g["C"].shape[0]
+    ctrl = MPC(3, 2, T, u_lower=-bound, u_upper=bound, lqr_iter=12, verbose=-1, grad_method=GradMethods.ANALYTIC,
+               exit_unconverged=False, detach_unconverged=False, eps=1e-6)
+    return ctrl(g["x_init"].to(DEV), QuadCost(g["C"].to(DEV), g["c"].to(DEV)), dx)
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_mpc_nn_dynamics_analytic_matches_reference(act):
+    g = load_golden(f"nn_dynamics_{act}_f64")
+    x, u, costs = solve(g, build_net(g, act).to(DEV), 0.6)
+    sc = max(1.0, float(g["x"].abs().max()))
+    assert maxdiff(u, g["u"]) < 1e-6 and maxdiff(x, g["x"]) < 1e-6 * sc
+    assert maxdiff(costs, g["costs"]) < 1e-7 * max(1.0, float(g["costs"].abs().max()))
+    assert torch.equal(u.abs().cpu() == 0.6, g["u"].abs() == 0.6)        # same controls on the bounds
+
+
+def test_mpc_affine_dynamics_analytic_matches_reference():
+    from mpc.dynamics import AffineDynamics
+    g = load_golden("affine_dynamics_f64")
+    dx = AffineDynamics(g["A"].to(DEV), g["B"].to(DEV), g["c0"].to(DEV))
+    x, u, costs = solve(g, dx, 0.5)
+    assert maxdiff(u, g["u"]) < 1e-7 and maxdiff(x, g["x"]) < 1e-7 * max(1.0, float(g["x"].abs().max()))
+    assert torch.equal(u.abs().cpu() == 0.5, g["u"].abs() == 0.5)
+
+
+def test_nn_dynamics_gradient_flows_to_the_weights():
+    """d loss / d weights through the controller (the reference's imitation-learning use, README): the final
+    differentiable LQR step sees F, f built from grad_input under autograd."""
+    from mpc.pytorch_b200 import MPC, QuadCost, GradMethods
+    g = load_golden("nn_dynamics_sigmoid_f64")
+    net = build_net(g, "sigmoid").to(DEV)
+    T = g["C"].shape[0]
+    ctrl = MPC(3, 2, T, lqr_iter=12, verbose=-1, grad_method=GradMethods.ANALYTIC, exit_unconverged=False,
+               detach_unconverged=False, eps=1e-6)
+    x, u, _ = ctrl(g["x_init"].to(DEV), QuadCost(g["C"].to(DEV), g["c"].to(DEV)), net)
+    u.pow(2).sum().backward()
+    gw = net.fcs[0].weight.grad
+    assert gw is not None and bool(torch.isfinite(gw).all()) and float(gw.abs().max()) > 0
