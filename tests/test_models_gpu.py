@@ -1,5 +1,11 @@
 """iLQR through learned / affine dynamics with GradMethods.ANALYTIC (grad_input Jacobians, reference
-mpc/mpc.py:495-524) vs trajectories of the unmodified reference (oracle/make_golden_nn.py), float64."""
+mpc/mpc.py:495-524) vs trajectories of the unmodified reference (oracle/make_golden_nn.py), float64.
+
+Tolerance: these are box-constrained solves, so the comparison is at pnqp's own accuracy - the reference stops its
+batched QP when the slowest element has |dx| < 1e-4 while the kernels stop per problem;
+SURVEY.md section 8(c) policy: x, u to 2e-4, costs (second order in that difference) to 1e-5 relative, and the set
+of controls sitting on a bound exactly."""
+TOL_XU, TOL_COST = 2e-4, 1e-5
 import pytest
 import torch
 
@@ -23,8 +29,8 @@ def test_mpc_nn_dynamics_analytic_matches_reference(act):
     g = load_golden(f"nn_dynamics_{act}_f64")
     x, u, costs = solve(g, build_net(g, act).to(DEV), 0.6)
     sc = max(1.0, float(g["x"].abs().max()))
-    assert maxdiff(u, g["u"]) < 1e-6 and maxdiff(x, g["x"]) < 1e-6 * sc
-    assert maxdiff(costs, g["costs"]) < 1e-7 * max(1.0, float(g["costs"].abs().max()))
+    assert maxdiff(u, g["u"]) < TOL_XU and maxdiff(x, g["x"]) < TOL_XU * sc
+    assert maxdiff(costs, g["costs"]) < TOL_COST * max(1.0, float(g["costs"].abs().max()))
     assert torch.equal(u.abs().cpu() == 0.6, g["u"].abs() == 0.6)        # same controls on the bounds
 
 
@@ -33,7 +39,8 @@ def test_mpc_affine_dynamics_analytic_matches_reference():
     g = load_golden("affine_dynamics_f64")
     dx = AffineDynamics(g["A"].to(DEV), g["B"].to(DEV), g["c0"].to(DEV))
     x, u, costs = solve(g, dx, 0.5)
-    assert maxdiff(u, g["u"]) < 1e-7 and maxdiff(x, g["x"]) < 1e-7 * max(1.0, float(g["x"].abs().max()))
+    assert maxdiff(u, g["u"]) < TOL_XU and maxdiff(x, g["x"]) < TOL_XU * max(1.0, float(g["x"].abs().max()))
+    assert maxdiff(costs, g["costs"]) < TOL_COST * max(1.0, float(g["costs"].abs().max()))
     assert torch.equal(u.abs().cpu() == 0.5, g["u"].abs() == 0.5)
 
 
