@@ -44,10 +44,14 @@ def main():
             x, u, costs = rmpc.MPC(n, m, T, u_lower=-0.6, u_upper=0.6, lqr_iter=12, verbose=-1,
                                    grad_method=rmpc.GradMethods.ANALYTIC, exit_unconverged=False,
                                    detach_unconverged=False, eps=1e-6)(x0, rmpc.QuadCost(C, c), net)
+        with contextlib.redirect_stdout(io.StringIO()):          # same problem without bounds: no QP tolerance involved
+            xf, uf, cf = rmpc.MPC(n, m, T, lqr_iter=12, verbose=-1, grad_method=rmpc.GradMethods.ANALYTIC,
+                                  exit_unconverged=False, detach_unconverged=False, eps=1e-6)(
+                x0, rmpc.QuadCost(C, c), net)
         ws = {f"W{i}": fc.weight for i, fc in enumerate(net.fcs)}
         ws.update({f"b{i}": fc.bias for i, fc in enumerate(net.fcs)})
         npz(f"nn_dynamics_{act}_f64", step_x=xs, step_u=us, step_next=nxt, R=R, S=S, C=C, c=c, x_init=x0,
-            x=x, u=u, costs=costs, n_layers=np.int64(len(net.fcs)), **ws)
+            x=x, u=u, costs=costs, x_free=xf, u_free=uf, costs_free=cf, n_layers=np.int64(len(net.fcs)), **ws)
         print(act, "clamped fraction", float((u.abs() == 0.6).double().mean()), "cost", float(costs.mean()))
     # affine dynamics: x' = A x + B u + c (one system shared by the batch)
     torch.manual_seed(9)

@@ -19,7 +19,8 @@ DEV = torch.device("cuda:0")
 def solve(g, dx, bound):
     from mpc.pytorch_b200 import MPC, QuadCost, GradMethods
     T = g["C"].shape[0]
-    ctrl = MPC(3, 2, T, u_lower=-bound, u_upper=bound, lqr_iter=12, verbose=-1, grad_method=GradMethods.ANALYTIC,
+    kw = {} if bound is None else dict(u_lower=-bound, u_upper=bound)
+    ctrl = MPC(3, 2, T, **kw, lqr_iter=12, verbose=-1, grad_method=GradMethods.ANALYTIC,
                exit_unconverged=False, detach_unconverged=False, eps=1e-6)
     return ctrl(g["x_init"].to(DEV), QuadCost(g["C"].to(DEV), g["c"].to(DEV)), dx)
 
@@ -32,6 +33,16 @@ def test_mpc_nn_dynamics_analytic_matches_reference(act):
     assert maxdiff(u, g["u"]) < TOL_XU and maxdiff(x, g["x"]) < TOL_XU * sc
     assert maxdiff(costs, g["costs"]) < TOL_COST * max(1.0, float(g["costs"].abs().max()))
     assert torch.equal(u.abs().cpu() == 0.6, g["u"].abs() == 0.6)        # same controls on the bounds
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_mpc_nn_dynamics_unbounded_matches_reference_tightly(act):
+    """No bounds, so no QP stopping tolerance: 12 iLQR iterations through the network agree to round-off."""
+    g = load_golden(f"nn_dynamics_{act}_f64")
+    x, u, costs = solve(g, build_net(g, act).to(DEV), None)
+    sc = max(1.0, float(g["x_free"].abs().max()))
+    assert maxdiff(u, g["u_free"]) < 1e-7 * sc and maxdiff(x, g["x_free"]) < 1e-7 * sc
+    assert maxdiff(costs, g["costs_free"]) < 1e-9 * max(1.0, float(g["costs_free"].abs().max()))
 
 
 def test_mpc_affine_dynamics_analytic_matches_reference():
