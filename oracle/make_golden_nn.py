@@ -73,3 +73,48 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def grad_cases():
+    """d u* / d c and d u* / d (first-layer bias) of the iLQR solution through NNDynamics, with and without a
+    slew-rate penalty, from the reference's own autograd (the quantities its tests
+    test_lqr_backward_cost_nn_dynamics_module_constrained[_slew] compare with finite differences,
+    tests/test_mpc.py:560-744).  Seeds are searched until the solution is strictly partially on the bounds."""
+    rmpc, _, _, _ = load_reference()
+    import ref_mpc.dynamics as rdyn
+    torch.set_default_dtype(torch.float64)
+    n, m, T, B = 2, 2, 3, 1
+    p = n + m
+    for tag, slew in (("nn_grad_f64", None), ("nn_grad_slew_f64", 1.0)):
+        for seed in range(50):
+            torch.manual_seed(seed)
+            net = rdyn.NNDynamics(n, m, hidden_sizes=[10, 10], activation="sigmoid").double()
+            Cf = 10.0 * torch.randn(T, B, p, p)
+            C = (Cf.transpose(-1, -2) @ Cf).requires_grad_(True)
+            c = (10.0 * torch.randn(T, B, p)).requires_grad_(True)
+            x0 = torch.randn(B, n)
+            with contextlib.redirect_stdout(io.StringIO()):
+                x, u, _ = rmpc.MPC(n, m, T, u_lower=-1.0, u_upper=1.0, lqr_iter=40, verbose=-1,
+                                   exit_unconverged=False, max_linesearch_iter=1, slew_rate_penalty=slew,
+                                   grad_method=rmpc.GradMethods.ANALYTIC)(x0, rmpc.QuadCost(C, c), net)
+            uf = u.reshape(-1)
+            on = uf.abs() == 1.0
+            if bool(on.any()) and bool((~on).any()):
+                break
+        else:
+            raise RuntimeError("no seed with a partially active solution")
+        rows_c, rows_b = [], []
+        for i in range(uf.numel()):
+            gc, gb = torch.autograd.grad(uf[i], [c, net.fcs[0].bias], retain_graph=True)
+            rows_c.append(gc.reshape(-1))
+            rows_b.append(gb.reshape(-1))
+        ws = {f"W{i}": fc.weight for i, fc in enumerate(net.fcs)}
+        ws.update({f"b{i}": fc.bias for i, fc in enumerate(net.fcs)})
+        npz(tag, C=C, c=c, x_init=x0, x=x, u=u, du_dc=torch.stack(rows_c), du_db0=torch.stack(rows_b),
+            n_layers=np.int64(len(net.fcs)), seed=np.int64(seed), **ws)
+        print(tag, "seed", seed, "on bound", int(on.sum()), "of", uf.numel(),
+              "max|du/dc|", float(torch.stack(rows_c).abs().max()), "max|du/db0|", float(torch.stack(rows_b).abs().max()))
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_NN_GRAD", "1") == "1":
+    grad_cases()

@@ -58,3 +58,17 @@ def test_affine_dynamics():
     aug = CtrlPassthroughDynamics(dx)                            # state [u_prev; x] (reference :133-156)
     out = aug(torch.cat((u, x), 1), 2 * u)
     assert torch.equal(out[:, :2], 2 * u) and torch.equal(out[:, 2:], dx(x, 2 * u))
+
+
+def test_nn_dynamics_pickles():
+    """The reference makes its MLP picklable by hand (mpc/dynamics.py:39-54); a plain Module round-trips as is."""
+    import io
+    from mpc.dynamics import NNDynamics
+    torch.manual_seed(1)
+    net = NNDynamics(3, 1, hidden_sizes=[8], activation="relu", passthrough=False)
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    net2 = torch.load(buf, weights_only=False)
+    x, u = torch.randn(4, 3), torch.randn(4, 1)
+    assert torch.equal(net(x, u), net2(x, u)) and net2.activation == "relu" and net2.passthrough is False
