@@ -525,6 +525,18 @@ def main():
             e2e_step(k, lti=True)
         torch.cuda.synchronize(dev)
         e2e_lti_s = time.perf_counter() - t0
+    # what the e2e number is bound by: the host->device copy rate of this box, measured with one large pinned copy
+    hb = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+    db = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    pcie = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        db.copy_(hb, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        pcie = max(pcie, hb.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del hb, db
     if world > 1:
         te = torch.tensor([e2e_s, e2e_lti_s], device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -553,6 +565,8 @@ def main():
         "blocks": len(block_ms), "block_ms": [round(x, 4) for x in block_ms],
         "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "solves/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "h2d_gbs_achieved": round(h2d * e2e_steps / e2e_s / 1e9, 2), "h2d_gbs_measured_peak": round(pcie, 2),
+                "bound": "PCIe host->device copy of the step's inputs (one 256 MB pinned copy measured on this box)",
                 "api": "mpc.pytorch_b200.LQRStep(...)(x_init,C,c,F,f), pinned host buffers, copy-in / run streams"},
         "e2e_lti": {"value": B * world * e2e_steps / e2e_lti_s, "unit": "solves/s",
                     "h2d_bytes_per_step": int(h2d - host[0]["F"].numel() * 4 + host_F0[0].numel() * 4),
