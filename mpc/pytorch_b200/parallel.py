@@ -49,3 +49,56 @@ def global_max(value, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
     return v[0]
+
+
+# ----------------------------------------------------------------------------------------------
+# host staging buffers: pinned memory on the GPU's own NUMA node
+# ----------------------------------------------------------------------------------------------
+def gpu_local_cpus(device):
+    """CPU ids the driver reports as local to `device` (NVML cpu affinity), restricted to this process'
+    allowed set; None when NVML / the PCI id is unavailable.  One process per GPU, so this is also the right
+    set to run the rank's host threads on."""
+    import os
+    try:
+        import pynvml
+        pr = torch.cuda.get_device_properties(device)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:                               # noqa: BLE001 - best effort: any failure means "do not pin"
+        return None
+
+
+class numa_local:
+    """``with numa_local(device): buf = t.pin_memory()`` - allocate (first-touch) host staging buffers while the
+    thread runs on the GPU's local cores, so the pinned pages live on the socket the GPU hangs off.  A copy from
+    the far socket crosses the inter-socket link and measured 35-43 GB/s here instead of 55 GB/s."""
+
+    def __init__(self, device):
+        self.cpus = gpu_local_cpus(device)
+        self.saved = None
+
+    def __enter__(self):
+        import os
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except OSError:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+
+
+def pin_local(t, device):
+    """Pinned host copy of `t` placed on `device`'s NUMA node (see numa_local)."""
+    with numa_local(device):
+        return t.cpu().pin_memory()
