@@ -1,6 +1,7 @@
-"""debug: one test_step_gpu case under a chosen kernel (MPCB200_KERNEL), per-problem status / qp_iters vs the oracle"""
-import sys, torch
-sys.path.insert(0, ".")
+"""Developer aid (lives under tests/ because it checks against the oracle): one test_step_gpu case under a kernel
+chosen by MPCB200_KERNEL, per-problem status / qp_iters vs the oracle.  python tests/debug_case.py [B]"""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import lqr_oracle as orc
 from tests.helpers import gen_problem, nominal_controls
 from mpc.pytorch_b200.step import lqr_step_raw
