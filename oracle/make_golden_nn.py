@@ -118,3 +118,53 @@ def grad_cases():
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_NN_GRAD", "1") == "1":
     grad_cases()
+
+
+def load_ref_env(modname):
+    """Import ref_mpc.env_dx.<modname> (needs matplotlib at import time: stubbed; imports `mpc.util` by its absolute
+    name: aliased to the reference only while importing)."""
+    import importlib
+    import types
+    load_reference()
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib.pyplot"].style = types.SimpleNamespace(use=lambda *a, **k: None)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "mpc" or k.startswith("mpc.")}
+    sys.modules["mpc"] = sys.modules["ref_mpc"]
+    sys.modules["mpc.util"] = sys.modules["ref_mpc.util"]
+    try:
+        env = importlib.import_module("ref_mpc.env_dx." + modname)
+    finally:
+        for k in [k for k in sys.modules if k == "mpc" or k.startswith("mpc.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return env
+
+
+def pendulum_case():
+    """Pendulum swing-up iLQR (reference mpc/env_dx/pendulum.py: `simple` model, bounds +-2, decay 0.2, 5 line-search
+    iterations), B=16, T=20, float64, AUTO_DIFF Jacobians, 15 iterations: trajectories of the unmodified reference."""
+    rmpc, _, _, _ = load_reference()
+    rpen = load_ref_env("pendulum")
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(3)
+    B, T = 16, 20
+    dx = rpen.PendulumDx(params=torch.tensor((10.0, 1.0, 1.0)))
+    th = (torch.rand(B) * 2 - 1) * np.pi
+    x0 = torch.stack((torch.cos(th), torch.sin(th), torch.rand(B) * 2 - 1), 1)
+    q, p = dx.get_true_obj()
+    Q = torch.diag(q.double()).repeat(T, B, 1, 1)
+    pp = p.double().repeat(T, B, 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        x, u, costs = rmpc.MPC(3, 1, T, u_lower=dx.lower, u_upper=dx.upper, lqr_iter=15, verbose=-1,
+                               exit_unconverged=False, detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
+                               max_linesearch_iter=dx.max_linesearch_iter, grad_method=rmpc.GradMethods.AUTO_DIFF,
+                               eps=dx.mpc_eps)(x0, rmpc.QuadCost(Q, pp), dx)
+    npz("pendulum_ilqr_f64", x_init=x0, q=q.double(), p=p.double(), x=x, u=u, costs=costs, lqr_iter=np.int64(15))
+    print("pendulum: clamped fraction", float((u.abs() == 2.0).double().mean()), "mean cost", float(costs.mean()))
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_PENDULUM", "1") == "1":
+    pendulum_case()

@@ -106,3 +106,26 @@ def test_gradients_flow_through_a_known_system():
                   detach_unconverged=False, grad_method=GradMethods.AUTO_DIFF, eps=1e-8)(x0, QuadCost(Q, pp), dx)
     (x.sum() + u.sum()).backward()
     assert params.grad is not None and bool(torch.isfinite(params.grad).all()) and float(params.grad.abs().sum()) > 0
+
+
+def test_pendulum_ilqr_matches_reference_fixture():
+    """Pendulum swing-up (reference mpc/env_dx/pendulum.py recipe: bounds +-2, decay 0.2, 5 line-search iterations,
+    eps 1e-3), B=16, T=20, float64, 15 iterations, AUTO_DIFF in the reference; here the known system runs inside the
+    kernels (rollout, exact Jacobians by dual numbers, line-search rollout).  Fixture: oracle/make_golden_nn.py."""
+    from mpc.pytorch_b200 import MPC, QuadCost, GradMethods
+    from mpc.env_dx.pendulum import PendulumDx
+    from tests.helpers import load_golden
+    g = load_golden("pendulum_ilqr_f64")
+    T, B = g["x"].shape[0], g["x"].shape[1]
+    dx = PendulumDx(params=torch.tensor((10.0, 1.0, 1.0), dtype=torch.float64))
+    Q = torch.diag(g["q"]).repeat(T, B, 1, 1).to(DEV)
+    p = g["p"].repeat(T, B, 1).to(DEV)
+    ctrl = MPC(3, 1, T, u_lower=dx.lower, u_upper=dx.upper, lqr_iter=int(g["lqr_iter"]), verbose=-1,
+               exit_unconverged=False, detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
+               max_linesearch_iter=dx.max_linesearch_iter, grad_method=GradMethods.AUTO_DIFF, eps=dx.mpc_eps)
+    x, u, costs = ctrl(g["x_init"].to(DEV), QuadCost(Q, p), dx)
+    rel = (costs.cpu() - g["costs"]).abs() / g["costs"].abs().clamp_min(1.0)
+    assert float(rel.max()) < 1e-7, float(rel.max())
+    assert maxdiff(u, g["u"]) < 1e-5 * max(1.0, float(g["u"].abs().max()))
+    assert maxdiff(x, g["x"]) < 1e-4 * max(1.0, float(g["x"].abs().max()))
+    assert torch.equal(u.abs().cpu() == 2.0, g["u"].abs() == 2.0)
