@@ -196,3 +196,27 @@ def test_mpc_solution_is_the_box_qp_optimum(bound):
     for b in range(B):
         xs, us = _condensed_box_lqr_scipy(C[:, b], c[:, b], F[:, b], f[:, b], x0[b], lo, hi)
         assert maxdiff(u[:, b], us) < 2e-4 and maxdiff(x[:, b], xs) < 2e-4
+
+
+def test_module_cost_equal_to_a_quadratic_reproduces_quadcost():
+    """A cost given as an nn.Module (reference mpc/mpc.py:258-262 `approximate_cost`, lqr_step.py:233-234 true_cost in
+    the line search) that happens to be the quadratic 1/2 tau' C tau + c' tau must give the QuadCost solution: the
+    second-order expansion is exact and the split-mode rollout evaluates the same numbers (float64)."""
+    from mpc.pytorch_b200 import MPC, QuadCost, LinDx
+    B, T, n, m = 6, 7, 4, 2
+    dt = torch.float64
+    Ct, ct, F, f, x0 = gen_problem(77, B, T, n, m, dt, False, True)
+    C0, c0 = Ct[0, 0].to(DEV), ct[0, 0].to(DEV)                  # one (C, c) for every t and problem
+
+    class Quad(torch.nn.Module):
+        def forward(self, tau):
+            return 0.5 * (tau * (tau @ C0.t())).sum(-1) + tau @ c0
+
+    C = C0.expand(T, B, n + m, n + m).contiguous()
+    c = c0.expand(T, B, n + m).contiguous()
+    kw = dict(u_lower=-0.3, u_upper=0.3, lqr_iter=6, verbose=-1, exit_unconverged=False, detach_unconverged=False)
+    dx = LinDx(F.to(DEV), f.to(DEV))
+    xa, ua, ca = MPC(n, m, T, **kw)(x0.to(DEV), QuadCost(C, c), dx)
+    xb, ub, cb = MPC(n, m, T, **kw)(x0.to(DEV), Quad(), dx)
+    assert maxdiff(ua, ub) < 1e-8 and maxdiff(xa, xb) < 1e-8 * max(1.0, float(xa.abs().max()))
+    assert maxdiff(ca, cb) < 1e-9 * max(1.0, float(ca.abs().max()))
