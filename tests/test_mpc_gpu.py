@@ -217,6 +217,6 @@ def test_module_cost_equal_to_a_quadratic_reproduces_quadcost():
     kw = dict(u_lower=-0.3, u_upper=0.3, lqr_iter=6, verbose=-1, exit_unconverged=False, detach_unconverged=False)
     dx = LinDx(F.to(DEV), f.to(DEV))
     xa, ua, ca = MPC(n, m, T, **kw)(x0.to(DEV), QuadCost(C, c), dx)
-    xb, ub, cb = MPC(n, m, T, **kw)(x0.to(DEV), Quad(), dx)
+    xb, ub, cb = MPC(n, m, T, n_batch=B, **kw)(x0.to(DEV), Quad(), dx)   # batch size cannot be inferred from a Module (reference :198-199)
     assert maxdiff(ua, ub) < 1e-8 and maxdiff(xa, xb) < 1e-8 * max(1.0, float(xa.abs().max()))
     assert maxdiff(ca, cb) < 1e-9 * max(1.0, float(ca.abs().max()))
