@@ -6,7 +6,6 @@ for n == 1); ``If`` is a 0/1 tensor of H's dtype; ``i`` is the iteration count o
 (the reference's batch-coupled loop returns when the slowest element converges).  Control flow is per
 problem (what the reference computes for n_batch == 1).
 """
-import ctypes
 
 import torch
 
